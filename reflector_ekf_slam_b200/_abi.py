@@ -1,7 +1,6 @@
 """ctypes mirror of include/rekf.h (struct rekf_options and the enums).
 
-Shared by the engine binding (engine.py) and — from the test side only — by oracle/pyoracle.py,
-which reuses the same options struct (oracle/rekf_oracle.h takes a `const rekf_options*`).
+Used by the engine binding (engine.py).  The struct is plain data; the test-side CPU checker reuses it.
 """
 import ctypes as C
 

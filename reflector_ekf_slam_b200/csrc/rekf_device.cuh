@@ -1,0 +1,99 @@
+// rekf_device.cuh — device-side data layout of the B200 EKF engine.
+//
+// One handle = a batch of S independent sessions (filters); every kernel is launched once for the
+// whole batch (blockIdx.z or blockIdx.x = session).  All control state that the reference keeps in
+// host members (state_.time, vt_, state_.mu.rows(), the ReflectorMatchResult) lives in SessionState
+// in HBM, so a whole HandleObservationMessage (reflector_ekf_slam.cc:229-368) is a fixed chain of
+// launches with capacity-sized grids and no host round trip; kernels read the live sizes (N, r, N2)
+// from SessionState and exit early.
+//
+// Internal state ordering (differs from the reference's [x y θ l0x l0y …] to keep every landmark
+// pair 16-byte aligned): slot 0,1,2 = x,y,θ; slot 3 = zero padding (row and column of Σ stay 0
+// under every kernel); landmark j occupies slots 4+2j, 5+2j.  Σ is stored dense, exactly symmetric,
+// fp64, row pitch `ld` (a multiple of 128 so tcgen05 tiles never straddle the buffer edge).
+// The reference ordering is restored at the C-ABI boundary (k_pack_sigma / k_pack_mu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rekf {
+
+constexpr int kPoseSlots = 4;
+constexpr int kSigmaTile = 128;   // Σ pitch granularity = tcgen05 output tile edge
+constexpr int kKBlock = 32;       // measurement-row (GEMM K) granularity: one 128-byte swizzle row of tf32
+constexpr int kCholNb = 32;       // Cholesky / TRSM block size
+constexpr int kWCols = 16;        // columns of W = L⁻¹·H·Σ solved per CTA
+
+enum : int {
+  FLAG_LANDMARK_CAPACITY = 1,     // augmentation would exceed max_landmarks: extra reflectors dropped
+  FLAG_NOT_SPD = 2,               // a pivot of S = HΣHᵀ+Q was not positive
+  FLAG_OBS_CAPACITY = 4,          // more observations in a frame than max_observations
+  FLAG_TCGEN05_TIMEOUT = 8        // an mbarrier wait in the tensor-core SYRK gave up (should never happen)
+};
+
+struct SessionState {
+  double time;          // state_.time
+  double vt[3];         // vt_ (reflector_ekf_slam.h:52-53)
+  double gps_innov_pad; // unused, keeps 8-byte fields together
+  int N;                // landmarks in the state: state_.mu.rows() == 3 + 2N
+  int m;                // observations in the current frame
+  int M;                // result.state_obs_match_ids.size()
+  int Mmap;             // result.map_obs_match_ids.size()
+  int N2;               // result.new_ids.size()
+  int r;                // measurement rows of this frame: 2(M+Mmap) (+3 with a GPS pose), 0 = no update
+  int flags;            // sticky FLAG_* bits
+  unsigned ticket;      // last-block-done counter (augment kernel)
+};
+
+// Where the current message comes from: the handle's device mailbox (host path) or device-resident
+// replay arrays indexed by a device-side step counter (no host traffic; CUDA-graph friendly).
+struct InputRef {
+  const double *odom;       // session s, step t: odom + s*odom_ss + t*4   -> (time, vx, vy, wz)
+  const double *obs_time;   // obs_time + s*time_ss + t
+  const float *obs_xy;      // obs_xy + s*xy_ss + t*m_stride*2
+  const int *obs_count;     // per-session counts (host path) or nullptr -> m_fixed
+  const double *gps;        // per session 4 doubles (flag, x, y, yaw) or nullptr
+  long long odom_ss, time_ss, xy_ss;
+  int m_stride, m_fixed;
+  const int *step;          // device step counter, nullptr -> 0
+  double *pose_out;         // optional: pose after the step, pose_out + s*pose_ss + t*3
+  long long pose_ss;
+};
+
+struct Layout {
+  int S;          // sessions
+  int Ncap;       // landmark capacity
+  int ncap;       // 4 + 2*Ncap
+  int ld;         // Σ / μ pitch, multiple of 128
+  int mcap;       // observation capacity per frame
+  int rcap;       // 2*mcap + 4 (3 GPS rows + pad)
+  int rld;        // round_up(rcap, 32): pitch of the Wᵀ panels (GEMM K extent)
+  int sld;        // pitch of the S / L buffer (rld + 8: one extra row carries ν)
+  int mapcap;
+  int odom_model;
+  double q_lin, q_ang, q_obs;   // linear_velocity_cov, angular_velocity_cov, observation_cov
+  SessionState *st;
+  double *mu;     // [S][ld]
+  double *sigma;  // [S][ld][ld]
+  // pre-loaded beacon map (sensor::Map), shared by all sessions
+  float *map_xy;  // [mapcap][2]
+  double *map_cov;// [mapcap][4] row-major 2x2
+  int *map_count; // device scalar
+  // per-frame scratch
+  int *state_pairs, *map_pairs, *new_ids;   // [S][mcap*2], [S][mcap*2], [S][mcap]
+  double *Hp;     // [S][rcap][4]  pose coefficients of each measurement row (4th unused)
+  double *Hl;     // [S][rcap][2]  landmark coefficients
+  int *Hslot;     // [S][rcap]     internal slot of the row's landmark, -1 = none
+  double *innov;  // [S][rcap]
+  double *Qd;     // [S][rcap]     diagonal of Q
+  double *Sbuf;   // [S][rld][sld] column-major lower triangle of S, then L; row r carries ν → L⁻¹ν
+  double *Dinv;   // [S][rld/32][32][32] inverses of L's diagonal blocks
+  float *Wt_hi, *Wt_lo;  // [S][ld][rld] tf32 hi/lo split of Wᵀ (K-major operands of the tcgen05 SYRK)
+  double *W64;    // [S][ld][rld] fp64 Wᵀ (REKF_COV_SIMT_F64 only, else nullptr)
+  int *step;      // device step counter for replay
+};
+
+__host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }
+__host__ __device__ inline int internal_dim(int N) { return kPoseSlots + 2 * N; }
+
+}  // namespace rekf

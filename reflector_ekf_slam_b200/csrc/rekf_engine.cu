@@ -1,0 +1,822 @@
+// rekf_engine.cu — host side of librekf_b200.so: handle, memory, launch chains and the C ABI of
+// include/rekf.h.  The only CUDA-free code in here is the landmark-map text I/O (cold path,
+// reference reflector_ekf_slam.cc:43-95 and ros_node.cc:75-140).  There is no CPU fallback: without a
+// CUDA device rekf_create() fails with REKF_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/rekf.h"
+#include "rekf_device.cuh"
+#include "rekf_kernels.cuh"
+#include "syrk_tcgen05.cuh"
+
+using namespace rekf;
+
+namespace {
+
+enum KernelId { K_ODOM = 0, K_FRONT, K_INNOV, K_CHOL, K_SOLVE, K_SYRK, K_AUGMENT, K_ADVANCE, K_COUNT };
+const char *kKernelNames[K_COUNT] = {"k_odometry", "k_observation_front", "k_innovation", "k_cholesky",
+                                     "k_solve_w", "k_syrk", "k_augment", "k_advance_step"};
+
+struct ProfRecord { int id; cudaEvent_t a, b; };
+
+}  // namespace
+
+struct rekf_handle {
+  rekf_options opts{};
+  Layout L{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int64_t launches = 0;
+  // device mailbox for host-delivered messages + pinned staging ring
+  char *mb_dev = nullptr;
+  char *mb_host = nullptr;
+  size_t mb_bytes = 0, off_odom = 0, off_time = 0, off_gps = 0, off_count = 0, off_xy = 0;
+  static constexpr int kSlots = 32;
+  cudaEvent_t slot_done[kSlots]{};
+  int slot = 0;
+  InputRef host_in{};
+  // staging for getters / setters
+  double *stage_dev = nullptr;
+  size_t stage_elems = 0;
+  // host copy of the beacon map
+  std::vector<float> map_xy;
+  std::vector<double> map_cov;
+  // timing
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool profiling = false;
+  std::vector<ProfRecord> prof;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_us[K_COUNT]{};
+  int prof_calls[K_COUNT]{};
+  // replay graph
+  cudaGraphExec_t step_graph = nullptr;
+  InputRef graph_in{};
+  // tcgen05 SYRK resources
+  SyrkTc tc{};
+  std::vector<void *> allocations;
+};
+
+namespace {
+
+int fail(rekf_handle *h, int code, const char *fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    h->err = buf;
+  }
+  return code;
+}
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(h, REKF_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int dev_alloc(rekf_handle *h, T **p, size_t count, bool zero = true) {
+  void *q = nullptr;
+  const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) return fail(h, REKF_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  if (zero) {
+    e = cudaMemsetAsync(q, 0, bytes, h->stream);
+    if (e != cudaSuccess) return fail(h, REKF_ERR_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  }
+  h->allocations.push_back(q);
+  *p = static_cast<T *>(q);
+  return 0;
+}
+
+cudaEvent_t take_event(rekf_handle *h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  rekf_handle *h;
+  int id;
+  cudaEvent_t a = nullptr;
+  ProfScope(rekf_handle *h_, int id_) : h(h_), id(id_) {
+    ++h->launches;
+    if (h->profiling) {
+      a = take_event(h);
+      cudaEventRecord(a, h->stream);
+    }
+  }
+  ~ProfScope() {
+    if (a) {
+      cudaEvent_t b = take_event(h);
+      cudaEventRecord(b, h->stream);
+      h->prof.push_back({id, a, b});
+    }
+  }
+};
+
+void drain_profile(rekf_handle *h) {
+  for (auto &rec : h->prof) {
+    cudaEventSynchronize(rec.b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, rec.a, rec.b);
+    h->prof_us[rec.id] += 1e3 * ms;
+    h->prof_calls[rec.id] += 1;
+    h->event_pool.push_back(rec.a);
+    h->event_pool.push_back(rec.b);
+  }
+  h->prof.clear();
+}
+
+size_t smem_front(const Layout &L) { return sizeof(int) * 2 * (size_t)L.mcap; }
+size_t smem_chol(const Layout &L) { return sizeof(double) * ((size_t)(L.rcap + 1) * kPS + (size_t)kCholNb * kPS); }
+size_t smem_solve(const Layout &L) { return sizeof(double) * (size_t)L.rld * kYS; }
+
+int launch_odometry(rekf_handle *h, const InputRef &in) {
+  ProfScope p(h, K_ODOM);
+  k_odometry<<<h->L.S, 1024, 0, h->stream>>>(h->L, in);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// HandleObservationMessage as a fixed launch chain; sizes are read on the device.
+int launch_observation(rekf_handle *h, const InputRef &in) {
+  const Layout &L = h->L;
+  {
+    ProfScope p(h, K_FRONT);
+    k_observation_front<<<L.S, 1024, smem_front(L), h->stream>>>(L, in);
+  }
+  {
+    ProfScope p(h, K_INNOV);
+    const int g = (L.rcap + 15) / 16;
+    k_innovation<<<dim3(g, g, L.S), dim3(16, 16), 0, h->stream>>>(L);
+  }
+  {
+    ProfScope p(h, K_CHOL);
+    k_cholesky<<<L.S, 1024, smem_chol(L), h->stream>>>(L);
+  }
+  {
+    ProfScope p(h, K_SOLVE);
+    k_solve_w<<<dim3(L.ld / kWCols, 1, L.S), 256, smem_solve(L), h->stream>>>(L);
+  }
+  {
+    ProfScope p(h, K_SYRK);
+    if (h->opts.cov_update == REKF_COV_SIMT_F64) {
+      k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);
+    } else {
+      int rc = syrk_tc_launch(h->tc, L, h->stream);
+      if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+  }
+  {
+    ProfScope p(h, K_AUGMENT);
+    k_augment<<<dim3((L.ncap + 255) / 256, 1, L.S), 256, 0, h->stream>>>(L, in);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int stage_reserve(rekf_handle *h, size_t elems) {
+  if (elems <= h->stage_elems) return 0;
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  h->stage_dev = nullptr;
+  h->stage_elems = 0;
+  cudaError_t e = cudaMalloc(&h->stage_dev, elems * sizeof(double));
+  if (e != cudaSuccess) return fail(h, REKF_ERR_CUDA, "cudaMalloc(stage %zu) failed: %s", elems * sizeof(double), cudaGetErrorString(e));
+  h->stage_elems = elems;
+  return 0;
+}
+
+int read_state(rekf_handle *h, int s, SessionState *out) {
+  if (s < 0 || s >= h->L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", s);
+  CK(cudaMemcpyAsync(out, h->L.st + s, sizeof(SessionState), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+// acquire the next pinned staging slot (waits only if the copy issued kSlots messages ago is pending)
+char *next_slot(rekf_handle *h) {
+  h->slot = (h->slot + 1) % rekf_handle::kSlots;
+  cudaEventSynchronize(h->slot_done[h->slot]);
+  return h->mb_host + (size_t)h->slot * h->mb_bytes;
+}
+
+// ---- landmark map text format ---------------------------------------------------------------
+// common.cc:5-16 SplitString = std::getline on ',' (empty tokens kept, trailing empty dropped)
+std::vector<std::string> split_commas(const std::string &line) {
+  std::istringstream ss(line);
+  std::string tok;
+  std::vector<std::string> out;
+  while (std::getline(ss, tok, ',')) out.push_back(tok);
+  return out;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+void rekf_default_options(rekf_options *o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->odom_model = REKF_ODOM_DIFF;              // ros_node.cc:285-296 default
+  o->linear_velocity_cov = 0.05 * 0.05;        // launch/slam.launch:21, squared at ros_node.cc:207-215
+  o->angular_velocity_cov = 0.08 * 0.08;       // launch/slam.launch:22
+  o->observation_cov = 0.05 * 0.05;            // launch/slam.launch:23
+  o->max_landmarks = 1024;
+  o->max_observations = 128;
+  o->max_map_landmarks = 1024;
+  o->cov_update = REKF_COV_TCGEN05_TF32X3;
+  o->map_loader = REKF_MAP_LOADER_FIXED;
+}
+
+const char *rekf_version(void) { return "rekf-b200 0.1 (sm_100a)"; }
+
+int rekf_create(const rekf_options *opts, rekf_handle **out) { return rekf_create_batch(opts, 1, out); }
+
+int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out) {
+  if (!opts || !out || sessions < 1) return REKF_ERR_BAD_ARGUMENT;
+  *out = nullptr;
+  rekf_handle *h = new rekf_handle();
+  *out = h;   // returned even on failure so that rekf_last_error() works; caller destroys it
+  h->opts = *opts;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(h, REKF_ERR_NO_DEVICE, "no CUDA device: %s (this library has no CPU path)", cudaGetErrorString(e));
+  if (opts->device < 0 || opts->device >= ndev) return fail(h, REKF_ERR_BAD_ARGUMENT, "device %d of %d", opts->device, ndev);
+  h->device = opts->device;
+  CK(cudaSetDevice(h->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10)
+    return fail(h, REKF_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", h->device, prop.major, prop.minor);
+  if (opts->stream) {
+    h->stream = static_cast<cudaStream_t>(opts->stream);
+  } else {
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  Layout &L = h->L;
+  L.S = sessions;
+  L.Ncap = opts->max_landmarks > 0 ? opts->max_landmarks : 1024;
+  L.mcap = opts->max_observations > 0 ? opts->max_observations : 128;
+  if (L.mcap > 512) return fail(h, REKF_ERR_BAD_ARGUMENT, "max_observations %d > 512", L.mcap);
+  L.mapcap = opts->max_map_landmarks > 0 ? opts->max_map_landmarks : 1024;
+  L.ncap = internal_dim(L.Ncap);
+  L.ld = round_up(L.ncap, kSigmaTile);
+  L.rcap = 2 * L.mcap + 4;
+  L.rld = round_up(L.rcap, kKBlock);
+  L.sld = L.rld + 8;
+  L.odom_model = opts->odom_model == REKF_ODOM_DIFF ? 0 : 1;   // :13-32: everything but DIFF is the 3x3 model
+  L.q_lin = opts->linear_velocity_cov;
+  L.q_ang = opts->angular_velocity_cov;
+  L.q_obs = opts->observation_cov;
+  const size_t S = (size_t)L.S;
+  int rc = 0;
+  if ((rc = dev_alloc(h, &L.st, S))) return rc;
+  if ((rc = dev_alloc(h, &L.mu, S * L.ld))) return rc;
+  if ((rc = dev_alloc(h, &L.sigma, S * L.ld * L.ld))) return rc;
+  if ((rc = dev_alloc(h, &L.map_xy, (size_t)L.mapcap * 2))) return rc;
+  if ((rc = dev_alloc(h, &L.map_cov, (size_t)L.mapcap * 4))) return rc;
+  if ((rc = dev_alloc(h, &L.map_count, 1))) return rc;
+  if ((rc = dev_alloc(h, &L.state_pairs, S * L.mcap * 2))) return rc;
+  if ((rc = dev_alloc(h, &L.map_pairs, S * L.mcap * 2))) return rc;
+  if ((rc = dev_alloc(h, &L.new_ids, S * L.mcap))) return rc;
+  if ((rc = dev_alloc(h, &L.Hp, S * L.rcap * 4))) return rc;
+  if ((rc = dev_alloc(h, &L.Hl, S * L.rcap * 2))) return rc;
+  if ((rc = dev_alloc(h, &L.Hslot, S * L.rcap))) return rc;
+  if ((rc = dev_alloc(h, &L.innov, S * L.rcap))) return rc;
+  if ((rc = dev_alloc(h, &L.Qd, S * L.rcap))) return rc;
+  if ((rc = dev_alloc(h, &L.Sbuf, S * L.rld * L.sld))) return rc;
+  if ((rc = dev_alloc(h, &L.Dinv, S * (L.rld / kCholNb) * kCholNb * kCholNb))) return rc;
+  if (opts->cov_update == REKF_COV_SIMT_F64) {
+    if ((rc = dev_alloc(h, &L.W64, S * L.ld * L.rld))) return rc;
+  } else if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
+    if ((rc = dev_alloc(h, &L.Wt_hi, S * L.ld * L.rld))) return rc;
+    if ((rc = dev_alloc(h, &L.Wt_lo, S * L.ld * L.rld))) return rc;
+  } else {
+    return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown cov_update %d", opts->cov_update);
+  }
+  if ((rc = dev_alloc(h, &L.step, 1))) return rc;
+
+  // initial state: time, pose (:8-11)
+  {
+    std::vector<SessionState> st(S);
+    std::vector<double> mu0(S * L.ld, 0.0);
+    for (size_t s = 0; s < S; ++s) {
+      std::memset(&st[s], 0, sizeof(SessionState));
+      st[s].time = opts->init_time;
+      for (int i = 0; i < 3; ++i) mu0[s * L.ld + i] = opts->init_pose[i];
+    }
+    CK(cudaMemcpyAsync(L.st, st.data(), sizeof(SessionState) * S, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(L.mu, mu0.data(), sizeof(double) * S * L.ld, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  // mailbox
+  h->off_odom = 0;
+  h->off_time = h->off_odom + S * 4 * sizeof(double);
+  h->off_gps = h->off_time + S * sizeof(double);
+  h->off_count = h->off_gps + S * 4 * sizeof(double);
+  h->off_xy = h->off_count + round_up((int)(S * sizeof(int)), 16);
+  h->mb_bytes = round_up((int)(h->off_xy + S * L.mcap * 2 * sizeof(float)), 256);
+  if ((rc = dev_alloc(h, &h->mb_dev, h->mb_bytes))) return rc;
+  CK(cudaMallocHost(&h->mb_host, h->mb_bytes * rekf_handle::kSlots));
+  std::memset(h->mb_host, 0, h->mb_bytes * rekf_handle::kSlots);
+  for (int i = 0; i < rekf_handle::kSlots; ++i) CK(cudaEventCreateWithFlags(&h->slot_done[i], cudaEventDisableTiming));
+  InputRef &in = h->host_in;
+  in.odom = reinterpret_cast<const double *>(h->mb_dev + h->off_odom);
+  in.obs_time = reinterpret_cast<const double *>(h->mb_dev + h->off_time);
+  in.gps = reinterpret_cast<const double *>(h->mb_dev + h->off_gps);
+  in.obs_count = reinterpret_cast<const int *>(h->mb_dev + h->off_count);
+  in.obs_xy = reinterpret_cast<const float *>(h->mb_dev + h->off_xy);
+  in.odom_ss = 4;
+  in.time_ss = 1;
+  in.xy_ss = (long long)L.mcap * 2;
+  in.m_stride = L.mcap;
+  in.m_fixed = 0;
+  in.step = nullptr;
+  in.pose_out = nullptr;
+  in.pose_ss = 0;
+  CK(cudaEventCreate(&h->t0));
+  CK(cudaEventCreate(&h->t1));
+  // opt in to large dynamic shared memory where needed
+  CK(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol(L)));
+  CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
+  if (smem_chol(L) > 227 * 1024) return fail(h, REKF_ERR_CAPACITY, "max_observations %d needs %zu B of shared memory in k_cholesky", L.mcap, smem_chol(L));
+  if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
+    const char *why = syrk_tc_init(h->tc, L);
+    if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK setup failed: %s", why);
+  }
+  if (opts->map_path && opts->map_path[0]) rekf_load_map_txt(h, opts->map_path);   // :36
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+int rekf_destroy(rekf_handle *h) {
+  if (!h) return REKF_OK;
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  drain_profile(h);
+  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  syrk_tc_destroy(h->tc);
+  for (void *p : h->allocations) cudaFree(p);
+  if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->mb_host) cudaFreeHost(h->mb_host);
+  for (auto &e : h->slot_done) if (e) cudaEventDestroy(e);
+  for (auto &e : h->event_pool) cudaEventDestroy(e);
+  if (h->t0) cudaEventDestroy(h->t0);
+  if (h->t1) cudaEventDestroy(h->t1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return REKF_OK;
+}
+
+const char *rekf_last_error(const rekf_handle *h) { return h ? h->err.c_str() : "null handle"; }
+int rekf_sessions(const rekf_handle *h) { return h ? h->L.S : 0; }
+int64_t rekf_launch_count(const rekf_handle *h) { return h ? h->launches : 0; }
+void *rekf_stream(rekf_handle *h) { return h ? h->stream : nullptr; }
+
+// ---- hot path -------------------------------------------------------------------------------
+int rekf_batch_handle_odometry(rekf_handle *h, const double *odom) {
+  if (!h || !odom) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaSetDevice(h->device));
+  if (h->opts.use_imu) return REKF_OK;   // :213-222: with use_imu the reference does nothing
+  char *slot = next_slot(h);
+  const size_t bytes = (size_t)h->L.S * 4 * sizeof(double);
+  std::memcpy(slot + h->off_odom, odom, bytes);
+  CK(cudaMemcpyAsync(h->mb_dev + h->off_odom, slot + h->off_odom, bytes, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->slot_done[h->slot], h->stream));
+  return launch_odometry(h, h->host_in);
+}
+
+int rekf_handle_odometry(rekf_handle *h, double time, double vx, double vy, double wz) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  if (h->L.S != 1) return fail(h, REKF_ERR_BAD_ARGUMENT, "rekf_handle_odometry needs a single-session handle");
+  const double msg[4] = {time, vx, vy, wz};
+  return rekf_batch_handle_odometry(h, msg);
+}
+
+static int observation_common(rekf_handle *h, const double *times, const float *xy, const int *counts,
+                              int m_stride, const double *gps /*S x 4 or null*/) {
+  const Layout &L = h->L;
+  CK(cudaSetDevice(h->device));
+  char *slot = next_slot(h);
+  std::memcpy(slot + h->off_time, times, sizeof(double) * L.S);
+  double *g = reinterpret_cast<double *>(slot + h->off_gps);
+  if (gps) std::memcpy(g, gps, sizeof(double) * 4 * L.S);
+  else std::memset(g, 0, sizeof(double) * 4 * L.S);
+  int *cnt = reinterpret_cast<int *>(slot + h->off_count);
+  float *dst = reinterpret_cast<float *>(slot + h->off_xy);
+  int max_m = 0;
+  for (int s = 0; s < L.S; ++s) {
+    const int m = counts[s];
+    if (m < 0) return fail(h, REKF_ERR_BAD_ARGUMENT, "negative observation count");
+    if (m > L.mcap) return fail(h, REKF_ERR_CAPACITY, "frame of %d observations exceeds max_observations %d", m, L.mcap);
+    cnt[s] = m;
+    max_m = std::max(max_m, m);
+    if (m > 0) std::memcpy(dst + (size_t)s * L.mcap * 2, xy + (size_t)s * m_stride * 2, sizeof(float) * 2 * m);
+  }
+  // one copy: time | gps | count | xy (only as far as the last session's data reaches)
+  const size_t end = h->off_xy + ((size_t)(L.S - 1) * L.mcap + (size_t)std::max(counts[L.S - 1], 0)) * 2 * sizeof(float);
+  CK(cudaMemcpyAsync(h->mb_dev + h->off_time, slot + h->off_time, end - h->off_time, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaEventRecord(h->slot_done[h->slot], h->stream));
+  (void)max_m;
+  return launch_observation(h, h->host_in);
+}
+
+int rekf_batch_handle_observation(rekf_handle *h, const double *times, const float *xy, const int *counts, int m_stride) {
+  if (!h || !times || !counts || (!xy && m_stride > 0)) return REKF_ERR_BAD_ARGUMENT;
+  return observation_common(h, times, xy, counts, m_stride, nullptr);
+}
+
+int rekf_handle_observation(rekf_handle *h, double time, const float *xy, int m, const double *gps_pose_or_null) {
+  if (!h || m < 0 || (m > 0 && !xy)) return REKF_ERR_BAD_ARGUMENT;
+  if (h->L.S != 1) return fail(h, REKF_ERR_BAD_ARGUMENT, "rekf_handle_observation needs a single-session handle");
+  double gps[4] = {0, 0, 0, 0};
+  if (gps_pose_or_null) { gps[0] = 1.0; gps[1] = gps_pose_or_null[0]; gps[2] = gps_pose_or_null[1]; gps[3] = gps_pose_or_null[2]; }
+  return observation_common(h, &time, xy, &m, m, gps_pose_or_null ? gps : nullptr);
+}
+
+int rekf_handle_imu(rekf_handle *h, double) { return h ? REKF_OK : REKF_ERR_BAD_ARGUMENT; }   // :224-227 empty
+
+int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_time, const void *d_obs_xy, int T, int m, void *d_pose_out) {
+  if (!h || !d_odom || !d_obs_time || !d_obs_xy || T < 0 || m < 0) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  if (m > L.mcap) return fail(h, REKF_ERR_CAPACITY, "m %d exceeds max_observations %d", m, L.mcap);
+  CK(cudaSetDevice(h->device));
+  InputRef in{};
+  in.odom = static_cast<const double *>(d_odom);
+  in.obs_time = static_cast<const double *>(d_obs_time);
+  in.obs_xy = static_cast<const float *>(d_obs_xy);
+  in.obs_count = nullptr;
+  in.gps = nullptr;
+  in.odom_ss = (long long)T * 4;
+  in.time_ss = T;
+  in.xy_ss = (long long)T * m * 2;
+  in.m_stride = m;
+  in.m_fixed = m;
+  in.step = L.step;
+  in.pose_out = static_cast<double *>(d_pose_out);
+  in.pose_ss = (long long)T * 3;
+  CK(cudaMemsetAsync(L.step, 0, sizeof(int), h->stream));
+  const bool graphs = h->opts.use_graphs && !h->profiling;
+  if (graphs) {
+    const bool same = h->step_graph && std::memcmp(&in, &h->graph_in, sizeof(InputRef)) == 0;
+    if (!same) {
+      if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = launch_odometry(h, in);
+      if (!rc) rc = launch_observation(h, in);
+      if (!rc) { ProfScope p(h, K_ADVANCE); k_advance_step<<<1, 1, 0, h->stream>>>(L.step); }
+      cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+      if (rc) return rc;
+      if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+      CK(cudaGraphInstantiate(&h->step_graph, g, 0));
+      cudaGraphDestroy(g);
+      h->graph_in = in;
+      h->launches -= K_COUNT;   // the capture pass itself launched nothing
+    }
+    for (int t = 0; t < T; ++t) CK(cudaGraphLaunch(h->step_graph, h->stream));
+    h->launches += (int64_t)T * K_COUNT;
+    return REKF_OK;
+  }
+  for (int t = 0; t < T; ++t) {
+    int rc = launch_odometry(h, in);
+    if (rc) return rc;
+    if ((rc = launch_observation(h, in))) return rc;
+    ProfScope p(h, K_ADVANCE);
+    k_advance_step<<<1, 1, 0, h->stream>>>(L.step);
+  }
+  CK(cudaGetLastError());
+  return REKF_OK;
+}
+
+// ---- accessors --------------------------------------------------------------------------------
+int rekf_sync(rekf_handle *h) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaStreamSynchronize(h->stream));
+  std::vector<SessionState> st(h->L.S);
+  CK(cudaMemcpy(st.data(), h->L.st, sizeof(SessionState) * h->L.S, cudaMemcpyDeviceToHost));
+  for (int s = 0; s < h->L.S; ++s) {
+    if (st[s].flags & FLAG_NOT_SPD) return fail(h, REKF_ERR_NOT_SPD, "session %d: innovation matrix not positive definite", s);
+    if (st[s].flags & FLAG_TCGEN05_TIMEOUT) return fail(h, REKF_ERR_CUDA, "session %d: tcgen05 SYRK barrier timeout", s);
+    if (st[s].flags & (FLAG_LANDMARK_CAPACITY | FLAG_OBS_CAPACITY)) return fail(h, REKF_ERR_CAPACITY, "session %d: capacity exceeded (flags %d)", s, st[s].flags);
+  }
+  return REKF_OK;
+}
+
+int rekf_device_error_flags(rekf_handle *h, int session, int *flags_out) {
+  if (!h || !flags_out) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  *flags_out = st.flags;
+  return REKF_OK;
+}
+
+int rekf_dim(rekf_handle *h, int session) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  return rc ? rc : 3 + 2 * st.N;
+}
+
+int rekf_time(rekf_handle *h, int session, double *time_out) {
+  if (!h || !time_out) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  *time_out = st.time;
+  return REKF_OK;
+}
+
+int rekf_get_mu(rekf_handle *h, int session, double *mu, int cap, int *n_out) {
+  if (!h || (!mu && cap > 0)) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  const int n = 3 + 2 * st.N;
+  if (n_out) *n_out = n;
+  const int c = std::min(n, cap);
+  if (c <= 0) return REKF_OK;
+  if ((rc = stage_reserve(h, n))) return rc;
+  k_pack_mu<<<(n + 255) / 256, 256, 0, h->stream>>>(h->L, session, h->stage_dev);
+  CK(cudaMemcpyAsync(mu, h->stage_dev, sizeof(double) * c, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) {
+  if (!h || !pose) return REKF_ERR_BAD_ARGUMENT;
+  if (session < 0 || session >= h->L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
+  const Layout &L = h->L;
+  CK(cudaMemcpyAsync(pose, L.mu + (size_t)session * L.ld, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  if (cov33)   // the block is symmetric, so row- vs column-major is immaterial
+    CK(cudaMemcpy2DAsync(cov33, sizeof(double) * 3, L.sigma + (size_t)session * L.ld * L.ld, sizeof(double) * L.ld,
+                         sizeof(double) * 3, 3, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, int cap, int *count_out) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  if (count_out) *count_out = st.N;
+  const int c = std::min(st.N, cap);
+  if (c <= 0) return REKF_OK;
+  if ((rc = stage_reserve(h, (size_t)st.N * 6))) return rc;
+  double *dxy = h->stage_dev, *dcov = h->stage_dev + (size_t)st.N * 2;
+  k_pack_landmarks<<<(st.N + 255) / 256, 256, 0, h->stream>>>(h->L, session, dxy, dcov);
+  if (xy) CK(cudaMemcpyAsync(xy, dxy, sizeof(double) * 2 * c, cudaMemcpyDeviceToHost, h->stream));
+  if (cov2x2) CK(cudaMemcpyAsync(cov2x2, dcov, sizeof(double) * 4 * c, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+int rekf_get_sigma(rekf_handle *h, int session, double *sigma, int ld) {
+  if (!h || !sigma) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  const int n = 3 + 2 * st.N;
+  if (ld < n) return fail(h, REKF_ERR_BAD_ARGUMENT, "ld %d < n %d", ld, n);
+  if ((rc = stage_reserve(h, (size_t)n * n))) return rc;
+  k_pack_sigma<<<dim3((n + 255) / 256, n), 256, 0, h->stream>>>(h->L, session, h->stage_dev, n);
+  CK(cudaMemcpy2DAsync(sigma, sizeof(double) * ld, h->stage_dev, sizeof(double) * n, sizeof(double) * n, n,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+int rekf_get_match_result(rekf_handle *h, int session, int *state_pairs, int *n_state, int *map_pairs, int *n_map,
+                          int *new_ids, int *n_new, int cap) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  const Layout &L = h->L;
+  if (n_state) *n_state = st.M;
+  if (n_map) *n_map = st.Mmap;
+  if (n_new) *n_new = st.N2;
+  if (state_pairs && st.M > 0)
+    CK(cudaMemcpy(state_pairs, L.state_pairs + (size_t)session * L.mcap * 2, sizeof(int) * 2 * std::min(st.M, cap), cudaMemcpyDeviceToHost));
+  if (map_pairs && st.Mmap > 0)
+    CK(cudaMemcpy(map_pairs, L.map_pairs + (size_t)session * L.mcap * 2, sizeof(int) * 2 * std::min(st.Mmap, cap), cudaMemcpyDeviceToHost));
+  if (new_ids && st.N2 > 0)
+    CK(cudaMemcpy(new_ids, L.new_ids + (size_t)session * L.mcap, sizeof(int) * std::min(st.N2, cap), cudaMemcpyDeviceToHost));
+  return REKF_OK;
+}
+
+int rekf_predict_state(rekf_handle *h, int session, double time, double *mu, int cap, double *sigma, int ld) {
+  if (!h || !mu) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  const int n = 3 + 2 * st.N;
+  if (cap < n || (sigma && ld < n)) return fail(h, REKF_ERR_BAD_ARGUMENT, "buffers too small for n = %d", n);
+  if ((rc = stage_reserve(h, (size_t)n * n + n))) return rc;
+  double *dmu = h->stage_dev, *dsig = sigma ? h->stage_dev + n : nullptr;
+  k_predict_state<<<dim3((n + 255) / 256, sigma ? n : 1), 256, 0, h->stream>>>(h->L, session, time, dmu, dsig, n);
+  CK(cudaMemcpyAsync(mu, dmu, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma)
+    CK(cudaMemcpy2DAsync(sigma, sizeof(double) * ld, dsig, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+// ---- state injection / persistence ----------------------------------------------------------------
+int rekf_set_state(rekf_handle *h, int session, double time, const double vt[3], const double *mu, int n, const double *sigma, int ld) {
+  if (!h || !mu || !sigma || n < 3 || ((n - 3) & 1) || ld < n) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  if (session < 0 || session >= L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
+  const int N = (n - 3) / 2;
+  if (N > L.Ncap) return fail(h, REKF_ERR_CAPACITY, "%d landmarks exceed max_landmarks %d", N, L.Ncap);
+  int rc = stage_reserve(h, (size_t)n * n + n);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(h->stream));
+  double *dmu = h->stage_dev, *dsig = h->stage_dev + n;
+  CK(cudaMemcpyAsync(dmu, mu, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpy2DAsync(dsig, sizeof(double) * n, sigma, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(L.sigma + (size_t)session * L.ld * L.ld, 0, sizeof(double) * L.ld * L.ld, h->stream));
+  CK(cudaMemsetAsync(L.mu + (size_t)session * L.ld, 0, sizeof(double) * L.ld, h->stream));
+  k_unpack_state<<<dim3((n + 255) / 256, n), 256, 0, h->stream>>>(L, session, dmu, dsig, n, n);
+  SessionState st;
+  std::memset(&st, 0, sizeof(st));
+  st.time = time;
+  if (vt) for (int i = 0; i < 3; ++i) st.vt[i] = vt[i];
+  st.N = N;
+  CK(cudaMemcpyAsync(L.st + session, &st, sizeof(st), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
+int rekf_set_map(rekf_handle *h, const float *xy, const double *cov2x2, int count) {
+  if (!h || count < 0 || (count > 0 && (!xy || !cov2x2))) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  if (count > L.mapcap) return fail(h, REKF_ERR_CAPACITY, "%d beacons exceed max_map_landmarks %d", count, L.mapcap);
+  h->map_xy.assign(xy, xy + 2 * (size_t)count);
+  h->map_cov.assign(cov2x2, cov2x2 + 4 * (size_t)count);
+  CK(cudaStreamSynchronize(h->stream));
+  if (count > 0) {
+    CK(cudaMemcpy(L.map_xy, xy, sizeof(float) * 2 * count, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(L.map_cov, cov2x2, sizeof(double) * 4 * count, cudaMemcpyHostToDevice));
+  }
+  CK(cudaMemcpy(L.map_count, &count, sizeof(int), cudaMemcpyHostToDevice));
+  return REKF_OK;
+}
+
+int rekf_get_map(rekf_handle *h, float *xy, double *cov2x2, int cap, int *count_out) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  const int n = (int)h->map_xy.size() / 2;
+  if (count_out) *count_out = n;
+  const int c = std::min(n, cap);
+  if (xy && c > 0) std::memcpy(xy, h->map_xy.data(), sizeof(float) * 2 * c);
+  if (cov2x2 && c > 0) std::memcpy(cov2x2, h->map_cov.data(), sizeof(double) * 4 * c);
+  return REKF_OK;
+}
+
+// LoadMapFromTxtFile (:43-95).  Missing file / wrong shape / unparsable token: silent no-op.
+int rekf_load_map_txt(rekf_handle *h, const char *path) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  if (!path || !path[0]) return REKF_OK;                       // :45
+  std::ifstream in(path);
+  if (!in.good()) return REKF_OK;                              // :45-46, :67-72
+  std::vector<std::vector<double>> rows;
+  std::string line;
+  while (std::getline(in, line)) {                             // :52
+    while (!line.empty() && (line.back() == '\r' || line.back() == '\n')) line.pop_back();
+    if (line.empty()) continue;                                // :55
+    std::vector<double> vec;
+    for (const auto &tok : split_commas(line)) {               // :58-62
+      char *end = nullptr;
+      const double v = std::strtod(tok.c_str(), &end);
+      if (end == tok.c_str()) return REKF_OK;                  // std::stod would throw; here: no-op
+      vec.push_back(v);
+    }
+    rows.push_back(vec);
+  }
+  if (rows.size() != 2 || rows[1].size() != 2 * rows[0].size()) return REKF_OK;   // :74
+  const int M_ = (int)rows[0].size() / 2;                      // :83
+  std::vector<float> xy(2 * (size_t)M_);
+  std::vector<double> cov(4 * (size_t)M_, 0.0);
+  for (int i = 0; i < M_; ++i) {                               // :85 double → float
+    xy[2 * i] = (float)rows[0][2 * i];
+    xy[2 * i + 1] = (float)rows[0][2 * i + 1];
+  }
+  for (int i = 0; i < M_; ++i)
+    for (int e = 0; e < 4; ++e) {
+      if (h->opts.map_loader == REKF_MAP_LOADER_REFERENCE) {   // :90 reads the positions line
+        const size_t idx = 4 * (size_t)i + e;
+        cov[4 * i + e] = idx < rows[0].size() ? rows[0][idx] : 0.0;
+      } else {
+        cov[4 * i + e] = rows[1][4 * (size_t)i + e];
+      }
+    }
+  return rekf_set_map(h, xy.data(), cov.data(), M_);           // :93-94
+}
+
+// Node::SaveReflectorResult (ros_node.cc:75-140): same two lines, default ostream formatting.
+int rekf_save_map_txt(rekf_handle *h, int session, const char *filebase) {
+  if (!h || !filebase) return REKF_ERR_BAD_ARGUMENT;
+  int N = 0;
+  int rc = rekf_get_landmarks(h, session, nullptr, nullptr, 0, &N);
+  if (rc) return rc;
+  std::vector<double> xy(2 * (size_t)std::max(N, 1)), cov(4 * (size_t)std::max(N, 1));
+  if (N > 0 && (rc = rekf_get_landmarks(h, session, xy.data(), cov.data(), N, nullptr))) return rc;
+  const std::string path = std::string(filebase) + ".txt";    // :80
+  std::ofstream out(path.c_str(), std::ios::out);
+  if (!out.good()) return fail(h, REKF_ERR_IO, "cannot open %s", path.c_str());
+  const int Mm = (int)h->map_xy.size() / 2;
+  for (int i = 0; i < Mm; ++i) {                               // :87-97
+    out << h->map_xy[2 * i] << "," << h->map_xy[2 * i + 1];
+    if (i != Mm - 1) out << ",";
+  }
+  if (N > 0) {                                                 // :98-110 (leading comma unconditional)
+    out << ",";
+    for (int i = 0; i < N; ++i) {
+      out << xy[2 * i] << "," << xy[2 * i + 1];
+      if (i != N - 1) out << ",";
+    }
+  }
+  out << std::endl;
+  for (int i = 0; i < Mm; ++i) {                               // :112-123
+    out << h->map_cov[4 * i] << "," << h->map_cov[4 * i + 1] << "," << h->map_cov[4 * i + 2] << "," << h->map_cov[4 * i + 3];
+    if (i != Mm - 1) out << ",";
+  }
+  if (N > 0) {                                                 // :124-137
+    out << ",";
+    for (int i = 0; i < N; ++i) {
+      out << cov[4 * i] << "," << cov[4 * i + 1] << "," << cov[4 * i + 2] << "," << cov[4 * i + 3];
+      if (i != N - 1) out << ",";
+    }
+  }
+  out << std::endl;
+  out.close();
+  return REKF_OK;
+}
+
+// ---- timing ---------------------------------------------------------------------------------------
+int rekf_timer_start(rekf_handle *h) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaEventRecord(h->t0, h->stream));
+  return REKF_OK;
+}
+int rekf_timer_stop(rekf_handle *h, float *ms) {
+  if (!h || !ms) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaEventRecord(h->t1, h->stream));
+  CK(cudaEventSynchronize(h->t1));
+  CK(cudaEventElapsedTime(ms, h->t0, h->t1));
+  return REKF_OK;
+}
+int rekf_profile_enable(rekf_handle *h, int enable) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaStreamSynchronize(h->stream));
+  drain_profile(h);
+  h->profiling = enable != 0;
+  if (enable) {
+    std::memset(h->prof_us, 0, sizeof(h->prof_us));
+    std::memset(h->prof_calls, 0, sizeof(h->prof_calls));
+  }
+  return REKF_OK;
+}
+int rekf_profile_read(rekf_handle *h, const char **names, double *mean_us, int *calls, int cap, int *count_out) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaStreamSynchronize(h->stream));
+  drain_profile(h);
+  int c = 0;
+  for (int k = 0; k < K_COUNT && c < cap; ++k) {
+    if (names) names[c] = (k == K_SYRK && h->opts.cov_update == REKF_COV_TCGEN05_TF32X3) ? "k_syrk_tcgen05" : (k == K_SYRK ? "k_syrk_f64" : kKernelNames[k]);
+    if (mean_us) mean_us[c] = h->prof_calls[k] ? h->prof_us[k] / h->prof_calls[k] : 0.0;
+    if (calls) calls[c] = h->prof_calls[k];
+    ++c;
+  }
+  if (count_out) *count_out = c;
+  return REKF_OK;
+}
+
+}  // extern "C"

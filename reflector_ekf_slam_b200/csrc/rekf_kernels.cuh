@@ -1,0 +1,831 @@
+// rekf_kernels.cuh — CUDA-core kernels of the EKF step (sm_100a).
+//
+//   k_odometry            HandleOdometryMessage          reflector_ekf_slam.cc:208-223 (+ Predict :154-206)
+//   k_observation_front   Predict + ReflectorMatch + H/z build   :229-304, :370-455
+//   k_innovation          S = H·Σ·Hᵀ + Q (5x5 block gathers)     :305
+//   k_cholesky            S = L·Lᵀ, L⁻¹ν, diagonal-block inverses (replaces .inverse(), :305)
+//   k_solve_w             W = L⁻¹·H·Σ (block gather + blocked TRSM), μ += Wᵀ·L⁻¹ν  (:305-307)
+//   k_syrk_f64            Σ −= Wᵀ·W on the fp64 pipe (reference-accuracy mode)     (:308)
+//   k_augment             landmark initialisation        :311-364
+//   k_pack_* / k_unpack_* layout conversion at the C-ABI boundary
+//
+// Algebra.  The reference forms K = ΣHᵀS⁻¹ and Σ − K·H·Σ with dense Eigen products.  With S = L·Lᵀ and
+// W = L⁻¹·(HΣ):  K·ν = Wᵀ·(L⁻¹ν)  and  K·H·Σ = Wᵀ·W, so the update is one rank-r symmetric downdate.
+// H has at most five non-zeros per row (3 pose columns + the landmark's 2, :272-275), so H·Σ is a gather
+// of five rows of Σ per measurement row and is never materialised outside shared memory.
+#pragma once
+#include "rekf_device.cuh"
+
+namespace rekf {
+
+// ---------------------------------------------------------------------------------------------
+// motion model (Predict, :154-206)
+// ---------------------------------------------------------------------------------------------
+struct MotionTerms {
+  double g02, g12;   // G_xi(0,2), G_xi(1,2)
+  double V[9];       // G_u·Qu·G_uᵀ top-left 3x3, row-major (symmetric)
+  double d[3];       // pose increment
+};
+
+__device__ inline MotionTerms motion_model(const Layout &L, const double vt[3], double theta, double dt) {
+  MotionTerms t;
+  const double vx = vt[0], vy = vt[1], w = vt[2];
+  double Gu[9];  // 3 x q row-major, q = 2 (DIFF) or 3 (OMNI)
+  double q[3];
+  int nq;
+  if (L.odom_model == 0) {  // DIFF :156-183
+    const double delta_theta = w * dt;
+    const double a = theta + delta_theta / 2;
+    double sa, ca;
+    sincos(a, &sa, &ca);
+    t.d[0] = vx * dt * ca;
+    t.d[1] = vx * dt * sa;
+    t.d[2] = delta_theta;
+    t.g02 = -vx * dt * sa;
+    t.g12 = vx * dt * ca;
+    Gu[0] = dt * ca; Gu[1] = -vx * dt * dt * sa / 2;
+    Gu[3] = dt * sa; Gu[4] = vx * dt * dt * ca / 2;
+    Gu[6] = 0;       Gu[7] = dt;
+    Gu[2] = Gu[5] = Gu[8] = 0;
+    q[0] = L.q_lin; q[1] = L.q_ang; q[2] = 0;
+    nq = 2;
+  } else {                  // OMNI :184-205
+    double sa, ca;
+    sincos(theta, &sa, &ca);
+    t.d[2] = w * dt;
+    t.d[0] = vx * dt * ca - vy * dt * sa;
+    t.d[1] = vx * dt * sa + vy * dt * ca;
+    t.g02 = -vx * dt * sa - vy * dt * ca;
+    t.g12 = vx * dt * ca - vy * dt * sa;
+    Gu[0] = dt * ca; Gu[1] = -dt * sa; Gu[2] = 0;
+    Gu[3] = dt * sa; Gu[4] = dt * ca;  Gu[5] = 0;
+    Gu[6] = 0;       Gu[7] = 0;        Gu[8] = dt;
+    q[0] = L.q_lin; q[1] = L.q_lin; q[2] = L.q_ang;
+    nq = 3;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0;
+      for (int k = 0; k < nq; ++k) s += Gu[i * 3 + k] * q[k] * Gu[j * 3 + k];
+      t.V[i * 3 + j] = s;
+    }
+  return t;
+}
+
+__device__ inline double wrap_angle(double a) {
+  double s, c;
+  sincos(a, &s, &c);
+  return atan2(s, c);   // :181 atan2(sin θ, cos θ)
+}
+
+// Σ ← G_xi·Σ·G_xiᵀ + G_u·Qu·G_uᵀ, μ[0:3] += d, θ wrapped — by one CTA, O(n).  G_xi is the identity
+// plus two entries, so only rows/columns 0 and 1 change: row 0 += g02·row 2, row 1 += g12·row 2 and
+// the mirrored columns (the two n³ products of :178/:202 reduce to this without changing a sum).
+__device__ inline void predict_cta(const Layout &L, int s, double dt) {
+  SessionState &st = L.st[s];
+  double *mu = L.mu + (size_t)s * L.ld;
+  double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  const int n = internal_dim(st.N);
+  const int ld = L.ld;
+  const double vt[3] = {st.vt[0], st.vt[1], st.vt[2]};
+  const double theta = mu[2];
+  const MotionTerms t = motion_model(L, vt, theta, dt);
+  for (int c = kPoseSlots + threadIdx.x; c < n; c += blockDim.x) {
+    const double s2 = Sg[(size_t)2 * ld + c];
+    const double v0 = Sg[c] + t.g02 * s2;
+    const double v1 = Sg[(size_t)ld + c] + t.g12 * s2;
+    Sg[c] = v0;
+    Sg[(size_t)ld + c] = v1;
+    Sg[(size_t)c * ld] = v0;
+    Sg[(size_t)c * ld + 1] = v1;
+  }
+  __syncthreads();   // everyone has read mu[2] / st before thread 0 rewrites them
+  if (threadIdx.x == 0) {
+    double P[9], T[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) P[i * 3 + j] = Sg[(size_t)i * ld + j];
+    // T = G3·P (rows), P' = T·G3ᵀ (columns)
+    for (int j = 0; j < 3; ++j) {
+      T[0 + j] = P[0 + j] + t.g02 * P[6 + j];
+      T[3 + j] = P[3 + j] + t.g12 * P[6 + j];
+      T[6 + j] = P[6 + j];
+    }
+    for (int i = 0; i < 3; ++i) {
+      P[i * 3 + 0] = T[i * 3 + 0] + t.g02 * T[i * 3 + 2];
+      P[i * 3 + 1] = T[i * 3 + 1] + t.g12 * T[i * 3 + 2];
+      P[i * 3 + 2] = T[i * 3 + 2];
+    }
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) {
+        const double v = P[i * 3 + j] + t.V[i * 3 + j];
+        Sg[(size_t)i * ld + j] = v;
+        Sg[(size_t)j * ld + i] = v;   // keep Σ exactly symmetric
+      }
+    mu[0] += t.d[0];
+    mu[1] += t.d[1];
+    mu[2] = wrap_angle(mu[2] + t.d[2]);
+  }
+  __syncthreads();
+}
+
+__device__ inline int current_step(const InputRef &in) { return in.step ? *in.step : 0; }
+
+// HandleOdometryMessage (:208-223): stale drop, latch vt_ BEFORE predicting, predict, set time.
+__global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in) {
+  const int s = blockIdx.x;
+  SessionState &st = L.st[s];
+  const double *msg = in.odom + (size_t)s * in.odom_ss + (size_t)current_step(in) * 4;
+  const double time = msg[0];
+  const double t_state = st.time;
+  __syncthreads();
+  if (time < t_state) return;                      // :211
+  if (threadIdx.x == 0) { st.vt[0] = msg[1]; st.vt[1] = msg[2]; st.vt[2] = msg[3]; }   // :216
+  __syncthreads();
+  predict_cta(L, s, time - t_state);               // :217-218
+  if (threadIdx.x == 0) st.time = time;            // :219
+}
+
+// ---------------------------------------------------------------------------------------------
+// observation front end: Predict (:232-234) + ReflectorMatch (:370-455) + measurement rows (:248-304)
+// ---------------------------------------------------------------------------------------------
+__device__ inline void warp_argmin(double &d, int &j) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const double od = __shfl_xor_sync(0xffffffffu, d, off);
+    const int oj = __shfl_xor_sync(0xffffffffu, j, off);
+    if (od < d || (od == d && oj < j)) { d = od; j = oj; }   // lowest index on exact ties
+  }
+}
+
+constexpr int kMatchNew = 0, kMatchState = 1, kMatchMap = 2;
+
+__global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in) {
+  extern __shared__ int sm_i[];
+  const int s = blockIdx.x;
+  SessionState &st = L.st[s];
+  const int t_idx = current_step(in);
+  const double time = in.obs_time[(size_t)s * in.time_ss + t_idx];
+  const float *xy = in.obs_xy + (size_t)s * in.xy_ss + (size_t)t_idx * in.m_stride * 2;
+  int m = in.obs_count ? in.obs_count[s] : in.m_fixed;
+  const double t_state = st.time;
+  const int flags0 = st.flags;
+  __syncthreads();
+  predict_cta(L, s, time - t_state);               // :232-233, no sign check on dt
+  int flag_add = 0;
+  if (m > L.mcap) { m = L.mcap; flag_add |= FLAG_OBS_CAPACITY; }
+  if (m < 0) m = 0;
+
+  int *kind = sm_i;                 // [mcap]
+  int *target = sm_i + L.mcap;      // [mcap]
+  const double *mu = L.mu + (size_t)s * L.ld;
+  const int N = st.N;
+  const int Mmap = *L.map_count;
+  const double px = mu[0], py = mu[1], th = mu[2];
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+
+  // --- ReflectorMatch: one warp per observation, lanes stride over landmarks -------------------
+  for (int i = warp; i < m; i += nwarps) {
+    // point_transformed_to_global_frame (:389-393): double arithmetic, float32 result
+    const double ox = (double)xy[2 * i], oy = (double)xy[2 * i + 1];
+    const float gx = (float)(ox * cs - oy * sn + px);
+    const float gy = (float)(ox * sn + oy * cs + py);
+    int k = kMatchNew, tgt = -1;
+    if (Mmap > 0) {                                // :401-425
+      double best = INFINITY;
+      int bj = 0x7fffffff;
+      for (int j = lane; j < Mmap; j += 32) {
+        const double *C = L.map_cov + 4 * j;
+        const float dfx = L.map_xy[2 * j] - gx, dfy = L.map_xy[2 * j + 1] - gy;   // :408 float subtraction
+        const double dx = (double)dfx, dy = (double)dfy;
+        const double t0 = dx * C[0] + dy * C[2], t1 = dx * C[1] + dy * C[3];
+        const double dist = sqrt(t0 * dx + t1 * dy);                               // :411 Σ not inverted
+        if (dist < best) { best = dist; bj = j; }
+      }
+      warp_argmin(best, bj);
+      if (best < 0.05) { k = kMatchMap; tgt = bj; }                                // :420
+    }
+    if (k == kMatchNew && N > 0) {                 // :426-451
+      double best = INFINITY;
+      int bj = 0x7fffffff;
+      for (int j = lane; j < N; j += 32) {
+        const double2 l = *reinterpret_cast<const double2 *>(mu + kPoseSlots + 2 * j);
+        const float dfx = gx - (float)l.x, dfy = gy - (float)l.y;                  // :431, :433
+        const double dx = (double)dfx, dy = (double)dfy;
+        const double dist = sqrt(dx * dx + dy * dy);                               // :437 Euclidean
+        if (dist < best) { best = dist; bj = j; }
+      }
+      warp_argmin(best, bj);
+      if (best < 0.6) { k = kMatchState; tgt = bj; }                               // :446
+    }
+    if (lane == 0) { kind[i] = k; target[i] = tgt; }
+  }
+  __syncthreads();
+
+  // --- ordered compaction: lists keep observation order like the push_backs at :422/:448/:452 --
+  int *sp = L.state_pairs + (size_t)s * L.mcap * 2;
+  int *mp = L.map_pairs + (size_t)s * L.mcap * 2;
+  int *nw = L.new_ids + (size_t)s * L.mcap;
+  __shared__ int counts[3];
+  if (threadIdx.x < 3) counts[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int k = kind[i];
+    int pos = 0;
+    for (int u = 0; u < i; ++u) pos += (kind[u] == k);
+    if (k == kMatchState) { sp[2 * pos] = i; sp[2 * pos + 1] = target[i]; }
+    else if (k == kMatchMap) { mp[2 * pos] = i; mp[2 * pos + 1] = target[i]; }
+    else nw[pos] = i;
+    atomicAdd(&counts[k], 1);
+  }
+  __syncthreads();
+  const int M = counts[kMatchState], Mm = counts[kMatchMap], N2 = counts[kMatchNew];
+  const int MM = M + Mm;
+  const double *gps = in.gps ? in.gps + 4 * s : nullptr;
+  const bool has_gps = gps && gps[0] != 0.0 && MM > 0;   // the GPS rows live inside `if (MM > 0)` (gps.cc:246,305)
+  const int r = MM > 0 ? 2 * MM + (has_gps ? 3 : 0) : 0;
+
+  // --- measurement rows: A_k (:272-273), B (:255), z − ẑ (:265-270), Q (:276) ----------------
+  double *Hp = L.Hp + (size_t)s * L.rcap * 4;
+  double *Hl = L.Hl + (size_t)s * L.rcap * 2;
+  int *Hslot = L.Hslot + (size_t)s * L.rcap;
+  double *innov = L.innov + (size_t)s * L.rcap;
+  double *Qd = L.Qd + (size_t)s * L.rcap;
+  for (int k = threadIdx.x; k < MM; k += blockDim.x) {
+    int i, slot;
+    double lx, ly;
+    if (k < M) {
+      i = sp[2 * k];
+      const int j = sp[2 * k + 1];
+      slot = kPoseSlots + 2 * j;
+      lx = mu[slot]; ly = mu[slot + 1];
+    } else {                                       // beacon read as float32 (:281-283), no B block (:300)
+      i = mp[2 * (k - M)];
+      const int j = mp[2 * (k - M) + 1];
+      slot = -1;
+      lx = (double)L.map_xy[2 * j]; ly = (double)L.map_xy[2 * j + 1];
+    }
+    const double dx = lx - px, dy = ly - py;
+    const double zh0 = dx * cs + dy * sn;
+    const double zh1 = -dx * sn + dy * cs;
+    double *a0 = Hp + 8 * k, *a1 = a0 + 4;
+    a0[0] = -cs; a0[1] = -sn; a0[2] = -dx * sn + dy * cs; a0[3] = 0;
+    a1[0] = sn;  a1[1] = -cs; a1[2] = -dx * cs - dy * sn; a1[3] = 0;
+    Hl[4 * k + 0] = cs;  Hl[4 * k + 1] = sn;
+    Hl[4 * k + 2] = -sn; Hl[4 * k + 3] = cs;
+    Hslot[2 * k] = slot; Hslot[2 * k + 1] = slot;
+    innov[2 * k] = (double)xy[2 * i] - zh0;
+    innov[2 * k + 1] = (double)xy[2 * i + 1] - zh1;
+    Qd[2 * k] = L.q_obs; Qd[2 * k + 1] = L.q_obs;
+  }
+  if (has_gps && threadIdx.x < 3) {                // reflector_ekf_slam_gps.cc:314-334
+    const int b = threadIdx.x, q = 2 * MM + b;
+    double *a = Hp + 4 * q;
+    a[0] = b == 0; a[1] = b == 1; a[2] = b == 2; a[3] = 0;
+    Hl[2 * q] = 0; Hl[2 * q + 1] = 0;
+    Hslot[q] = -1;
+    if (b < 2) {
+      innov[q] = gps[1 + b] - (b == 0 ? px : py);
+      Qd[q] = 0.05 * 0.05;
+    } else {
+      const double dth = gps[3] - th;
+      double qz, qw;
+      sincos(dth / 2, &qz, &qw);
+      const double nrm = sqrt(qw * qw + qz * qz);
+      qw /= nrm; qz /= nrm;
+      if (qw < 0.) { qw = -qw; qz = -qz; }
+      const double angle = 2. * atan2(fabs(qz), qw);
+      const double scale = angle < 1e-7 ? 2. : angle / sin(angle / 2.);
+      innov[q] = scale * qz;
+      Qd[q] = 0.017 * 0.017;
+    }
+  }
+  if (threadIdx.x == 0) {
+    st.time = time;                                // :234
+    st.m = m; st.M = M; st.Mmap = Mm; st.N2 = N2; st.r = r;
+    st.flags = flags0 | flag_add;
+    st.ticket = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// S = H·Σ·Hᵀ + Q (lower triangle) and the ν row
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_innovation(Layout L) {
+  const int s = blockIdx.z;
+  const SessionState &st = L.st[s];
+  const int r = st.r;
+  const int q = blockIdx.x * 16 + threadIdx.x;   // row
+  const int p = blockIdx.y * 16 + threadIdx.y;   // column
+  if (r == 0 || q >= r || p > q) return;
+  const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  const double *Hp = L.Hp + (size_t)s * L.rcap * 4;
+  const double *Hl = L.Hl + (size_t)s * L.rcap * 2;
+  const int *Hslot = L.Hslot + (size_t)s * L.rcap;
+  const int ld = L.ld;
+  int ia[5], ib[5];
+  double ha[5], hb[5];
+  const int sq = Hslot[q], spp = Hslot[p];
+  for (int u = 0; u < 3; ++u) { ia[u] = u; ha[u] = Hp[4 * q + u]; ib[u] = u; hb[u] = Hp[4 * p + u]; }
+  const int na = sq >= 0 ? 5 : 3, nb = spp >= 0 ? 5 : 3;
+  if (sq >= 0) { ia[3] = sq; ia[4] = sq + 1; ha[3] = Hl[2 * q]; ha[4] = Hl[2 * q + 1]; }
+  if (spp >= 0) { ib[3] = spp; ib[4] = spp + 1; hb[3] = Hl[2 * p]; hb[4] = Hl[2 * p + 1]; }
+  double acc = 0;
+  for (int b = 0; b < nb; ++b) {       // ((H·Σ)·Hᵀ): y_b = Σ_a H[q,a]·Σ[a,b]
+    double y = 0;
+    for (int a = 0; a < na; ++a) y += ha[a] * Sg[(size_t)ia[a] * ld + ib[b]];
+    acc += y * hb[b];
+  }
+  if (p == q) acc += L.Qd[(size_t)s * L.rcap + q];
+  double *Sb = L.Sbuf + (size_t)s * L.rld * L.sld;
+  Sb[(size_t)p * L.sld + q] = acc;
+  if (p == 0) Sb[(size_t)q * L.sld + r] = L.innov[(size_t)s * L.rcap + q];   // ν as row r: Cholesky turns it into L⁻¹ν
+}
+
+// ---------------------------------------------------------------------------------------------
+// blocked left-looking Cholesky of S in one CTA; row r (ν) rides along and leaves as L⁻¹ν.
+// Also emits the inverse of every 32x32 diagonal block of L for the TRSM in k_solve_w.
+// ---------------------------------------------------------------------------------------------
+constexpr int kPS = kCholNb + 1;   // padded panel pitch in shared memory
+
+__global__ void __launch_bounds__(1024, 1) k_cholesky(Layout L) {
+  extern __shared__ double sm_d[];
+  const int s = blockIdx.x;
+  SessionState &st = L.st[s];
+  const int r = st.r;
+  if (r == 0) return;
+  const int sld = L.sld;
+  double *Sb = L.Sbuf + (size_t)s * L.rld * sld;
+  double *P = sm_d;                                  // [(rcap+1)][kPS] current block column (rows J..r)
+  double *X = sm_d + (size_t)(L.rcap + 1) * kPS;     // [32][kPS] inverse of the diagonal block
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  bool bad = false;
+
+  for (int J = 0; J < r; J += kCholNb) {
+    const int jb = min(kCholNb, r - J);
+    const int rows = r - J + 1;                      // incl. the ν row
+    // load the block column (lower part)
+    for (int e = tid; e < rows * jb; e += NT) {
+      const int jj = e / rows, i = e - jj * rows;
+      P[i * kPS + jj] = (i >= jj) ? Sb[(size_t)(J + jj) * sld + J + i] : 0.0;
+    }
+    __syncthreads();
+    // left-looking update with the finished columns 0..J-1:  P[i][jj] -= Σ_k L[J+i][k]·L[J+jj][k]
+    if (J > 0) {
+      for (int task = tid; task < rows * 4; task += NT) {
+        const int jg = task / rows, i = task - jg * rows;
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+        const double *Li = Sb + J + i;
+        const double *Lj = Sb + J + jg * 8;
+#pragma unroll 2
+        for (int k = 0; k < J; ++k) {
+          const double li = Li[(size_t)k * sld];
+          const double *lj = Lj + (size_t)k * sld;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] = fma(li, lj[u], acc[u]);   // lj[u] beyond jb hits finished rows: harmless
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int jj = jg * 8 + u;
+          if (jj < jb && i >= jj) P[i * kPS + jj] -= acc[u];
+        }
+      }
+      __syncthreads();
+    }
+    // factor the jb x jb diagonal block (right-looking, two barriers per column)
+    {
+      const int i = tid & 31, jj = tid >> 5;         // element (i, jj) of the block
+      const bool mine = (i < jb && jj < jb && i >= jj);
+      for (int j = 0; j < jb; ++j) {
+        const double d = P[j * kPS + j];
+        if (!(d > 0.0)) bad = true;
+        const double inv = rsqrt(d);
+        double li = 0, lj = 0;
+        if (mine && jj >= j) { li = P[i * kPS + j]; lj = P[jj * kPS + j]; }
+        __syncthreads();
+        if (mine) {
+          if (jj == j) P[i * kPS + j] = (i == j) ? d * inv : li * inv;
+          else if (jj > j) P[i * kPS + jj] -= (li * inv) * (lj * inv);
+        }
+        __syncthreads();
+      }
+    }
+    // X = D⁻¹ (lower triangular): warp c owns column c, lane i owns X[i][c]; column-oriented substitution
+    if (warp < jb) {
+      const int c = warp;
+      const double dii = (lane < jb) ? P[lane * kPS + lane] : 1.0;
+      const double invd = 1.0 / dii;
+      double t = (lane == c) ? 1.0 : 0.0;            // running rhs for row `lane`
+      double x = 0.0;
+      for (int k = c; k < jb; ++k) {
+        const double xk = __shfl_sync(0xffffffffu, t * invd, k);   // lane k finalises x_k = t_k / D[k][k]
+        if (lane == k) x = xk;
+        if (lane > k && lane < jb) t = fma(-P[lane * kPS + k], xk, t);
+      }
+      if (lane < jb) X[lane * kPS + c] = (lane >= c) ? x : 0.0;
+    } else if (warp < kCholNb) {
+      if (lane < kCholNb) X[lane * kPS + warp] = 0.0;
+    }
+    __syncthreads();
+    // rows below the diagonal block (incl. ν): P[i][:] ← P[i][:]·D⁻ᵀ, i.e. out[jj] = Σ_{k<=jj} P[i][k]·X[jj][k]
+    // Four threads per row (8 columns each); results are held in registers across a barrier because a
+    // row's threads read entries their neighbours overwrite.
+    {
+      const int below = rows - jb;
+      for (int base = 0; base < below * 4; base += NT) {   // tasks of one row never straddle a pass (NT % 4 == 0)
+        const int task = base + tid;
+        const bool act = task < below * 4;
+        const int i = jb + (task >> 2), jg = task & 3;
+        double out[8];
+        if (act) {
+          const double *row = P + i * kPS;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int jj = jg * 8 + u;
+            const double *x = X + jj * kPS;
+            double a0 = 0.0, a1 = 0.0;
+            if (jj < jb) {
+              int k = 0;
+              for (; k + 1 <= jj; k += 2) { a0 = fma(row[k], x[k], a0); a1 = fma(row[k + 1], x[k + 1], a1); }
+              if (k <= jj) a0 = fma(row[k], x[k], a0);
+            }
+            out[u] = a0 + a1;
+          }
+        }
+        __syncthreads();
+        if (act) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int jj = jg * 8 + u;
+            if (jj < jb) P[i * kPS + jj] = out[u];
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // write the finished block column of L and the block inverse
+    for (int e = tid; e < rows * jb; e += NT) {
+      const int jj = e / rows, i = e - jj * rows;
+      if (i >= jj) Sb[(size_t)(J + jj) * sld + J + i] = P[i * kPS + jj];
+    }
+    double *Dg = L.Dinv + ((size_t)s * (L.rld / kCholNb) + J / kCholNb) * kCholNb * kCholNb;
+    for (int e = tid; e < kCholNb * kCholNb; e += NT) {
+      const int i = e >> 5, k = e & 31;
+      Dg[e] = (i < jb && k < jb) ? X[i * kPS + k] : 0.0;
+    }
+    __syncthreads();
+  }
+  if (bad && tid == 0) atomicOr(&st.flags, FLAG_NOT_SPD);
+}
+
+// ---------------------------------------------------------------------------------------------
+// W = L⁻¹·(H·Σ) for 16 columns per CTA: block-gather from Σ into shared memory, blocked forward
+// substitution, then   μ[c] += Σ_k W[k][c]·(L⁻¹ν)[k]   and the tf32 hi/lo (or fp64) panels of Wᵀ.
+// ---------------------------------------------------------------------------------------------
+constexpr int kYS = kWCols + 1;    // padded pitch of the Y/W block in shared memory
+
+__device__ inline float to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256) k_solve_w(Layout L) {
+  extern __shared__ double sm_d[];
+  const int s = blockIdx.z;
+  const SessionState &st = L.st[s];
+  const int r = st.r;
+  if (r == 0) return;
+  const int n = internal_dim(st.N);
+  const int c0 = blockIdx.x * kWCols;
+  if (c0 >= round_up(n, kSigmaTile)) return;         // beyond the tiles the SYRK will touch
+  const int ld = L.ld, sld = L.sld, rld = L.rld;
+  const double *Sg = L.sigma + (size_t)s * ld * ld;
+  const double *Sb = L.Sbuf + (size_t)s * rld * sld;
+  const double *Hp = L.Hp + (size_t)s * L.rcap * 4;
+  const double *Hl = L.Hl + (size_t)s * L.rcap * 2;
+  const int *Hslot = L.Hslot + (size_t)s * L.rcap;
+  double *Y = sm_d;                                  // [rld][kYS]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  // gather: Y[q][cc] = Σ_b H[q][b]·Σ[b][c]  (Σ symmetric: read row c)
+  for (int cc = warp; cc < kWCols; cc += 8) {
+    const int c = c0 + cc;
+    if (c < n) {
+      const double *rowc = Sg + (size_t)c * ld;
+      const double p0 = rowc[0], p1 = rowc[1], p2 = rowc[2];
+      for (int q = lane; q < r; q += 32) {
+        const double *h = Hp + 4 * q;
+        double y = h[0] * p0 + h[1] * p1 + h[2] * p2;
+        const int slot = Hslot[q];
+        if (slot >= 0) {
+          const double2 v = *reinterpret_cast<const double2 *>(rowc + slot);
+          y += Hl[2 * q] * v.x + Hl[2 * q + 1] * v.y;
+        }
+        Y[q * kYS + cc] = y;
+      }
+    } else {
+      for (int q = lane; q < r; q += 32) Y[q * kYS + cc] = 0.0;
+    }
+  }
+  __syncthreads();
+
+  // blocked forward substitution L·W = Y
+  const double *Dinv = L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb;
+  for (int J = 0; J < r; J += kCholNb) {
+    const int jb = min(kCholNb, r - J);
+    const double *Dg = Dinv + (size_t)(J / kCholNb) * kCholNb * kCholNb;
+    // W_J = D_J⁻¹·Y_J : 32x16 outputs, two per thread
+    const int cc = tid & 15;
+    double w[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = (tid >> 4) + 16 * h;
+      double a = 0.0;
+      if (i < jb)
+        for (int k = 0; k <= i; ++k) a = fma(Dg[i * kCholNb + k], Y[(J + k) * kYS + cc], a);
+      w[h] = a;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = (tid >> 4) + 16 * h;
+      if (i < jb) Y[(J + i) * kYS + cc] = w[h];
+    }
+    __syncthreads();
+    // trailing rows: Y[i2][:] -= L[i2][J..J+jb)·W_J
+    const int below = r - (J + jb);
+    for (int task = tid; task < below * 4; task += blockDim.x) {
+      const int cg = task / below, i2 = J + jb + (task - cg * below);
+      double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      const double *Lr = Sb + (size_t)J * sld + i2;
+      for (int k = 0; k < jb; ++k) {
+        const double l = Lr[(size_t)k * sld];
+        const double *wk = Y + (J + k) * kYS + cg * 4;
+        a0 = fma(l, wk[0], a0); a1 = fma(l, wk[1], a1); a2 = fma(l, wk[2], a2); a3 = fma(l, wk[3], a3);
+      }
+      double *y = Y + i2 * kYS + cg * 4;
+      y[0] -= a0; y[1] -= a1; y[2] -= a2; y[3] -= a3;
+    }
+    __syncthreads();
+  }
+
+  // μ += Wᵀ·(L⁻¹ν)  (:306), θ wrapped (:307)
+  double *mu = L.mu + (size_t)s * ld;
+  for (int cc = warp; cc < kWCols; cc += 8) {
+    const int c = c0 + cc;
+    double a = 0.0;
+    for (int k = lane; k < r; k += 32) a = fma(Y[k * kYS + cc], Sb[(size_t)k * sld + r], a);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    if (lane == 0 && c < n) {
+      const double v = mu[c] + a;
+      mu[c] = (c == 2) ? wrap_angle(v) : v;
+    }
+  }
+  // Wᵀ panels (row c, K contiguous), zero beyond r
+  if (L.W64) {
+    double *W = L.W64 + (size_t)s * ld * rld;
+    for (int e = tid; e < kWCols * rld; e += blockDim.x) {
+      const int cc = e / rld, k = e - cc * rld;
+      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kYS + cc] : 0.0;
+    }
+  } else {
+    float *Wh = L.Wt_hi + (size_t)s * ld * rld, *Wl = L.Wt_lo + (size_t)s * ld * rld;
+    for (int e = tid; e < kWCols * rld; e += blockDim.x) {
+      const int cc = e / rld, k = e - cc * rld;
+      const double w = (k < r) ? Y[k * kYS + cc] : 0.0;
+      const float hi = to_tf32((float)w);
+      const float lo = to_tf32((float)(w - (double)hi));
+      Wh[(size_t)(c0 + cc) * rld + k] = hi;
+      Wl[(size_t)(c0 + cc) * rld + k] = lo;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Σ −= Wᵀ·W on the fp64 pipe: 64x64 upper-triangular tiles, mirrored (exact symmetry by construction)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
+  const int s = blockIdx.z;
+  const SessionState &st = L.st[s];
+  const int r = st.r;
+  const int ti = blockIdx.y, tj = blockIdx.x;
+  if (r == 0 || ti > tj) return;
+  const int n = internal_dim(st.N);
+  const int i0 = ti * 64, j0 = tj * 64;
+  if (j0 >= n) return;
+  const int rld = L.rld, ld = L.ld;
+  const double *W = L.W64 + (size_t)s * ld * rld;
+  double *Sg = L.sigma + (size_t)s * ld * ld;
+  __shared__ double As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+  for (int k0 = 0; k0 < r; k0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int row = e >> 4, kk = e & 15;
+      As[kk][row] = W[(size_t)(i0 + row) * rld + k0 + kk];   // rld is zero-padded past r
+      Bs[kk][row] = W[(size_t)(j0 + row) * rld + k0 + kk];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a[u] = As[kk][ty * 4 + u]; b[u] = Bs[kk][tx * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
+      if (i < n && j < n && i <= j) {
+        const double val = Sg[(size_t)i * ld + j] - acc[u][v];
+        Sg[(size_t)i * ld + j] = val;
+        Sg[(size_t)j * ld + i] = val;
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// augmentation (:311-364) + end-of-step bookkeeping
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
+  const int s = blockIdx.z;
+  SessionState &st = L.st[s];
+  const int t_idx = current_step(in);
+  const int N = st.N;
+  int N2 = st.N2;
+  bool overflow = false;
+  if (N + N2 > L.Ncap) { N2 = max(0, L.Ncap - N); overflow = true; }
+  const int n = internal_dim(N);
+  const int ld = L.ld;
+  double *Sg = L.sigma + (size_t)s * ld * ld;
+  double *mu = L.mu + (size_t)s * ld;
+  const float *xy = in.obs_xy + (size_t)s * in.xy_ss + (size_t)t_idx * in.m_stride * 2;
+  const int *nw = L.new_ids + (size_t)s * L.mcap;
+  if (N2 > 0) {
+    const double px = mu[0], py = mu[1], th = mu[2];   // post-update pose (:323-331)
+    double sn, cs;
+    sincos(th, &sn, &cs);
+    // cross blocks: Σ[new rows][c] = G_p·Σ[0:3][c]  (:355-357), c over the old state
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) {
+      const double s0 = Sg[c], s1 = Sg[(size_t)ld + c], s2 = Sg[(size_t)2 * ld + c];
+      for (int q = 0; q < N2; ++q) {
+        const int i = nw[q];
+        const double rx = (double)xy[2 * i], ry = (double)xy[2 * i + 1];   // :344-345
+        const double g0 = -rx * sn - ry * cs, g1 = rx * cs - ry * sn;       // :347
+        const double v0 = s0 + g0 * s2;     // [1 0 g0]·Σ[0:3][c]
+        const double v1 = s1 + g1 * s2;     // [0 1 g1]·Σ[0:3][c]
+        const int slot = n + 2 * q;
+        Sg[(size_t)slot * ld + c] = v0;
+        Sg[(size_t)(slot + 1) * ld + c] = v1;
+        Sg[(size_t)c * ld + slot] = v0;
+        Sg[(size_t)c * ld + slot + 1] = v1;
+      }
+    }
+    if (blockIdx.x == 0) {
+      // new-new blocks: G_p·Σ_xx·G_pᵀ + G_z·Qt·G_zᵀ (:354); G_z stacks the same rotation, so every
+      // 2x2 block — off-diagonal ones too — receives R(θ)·Qt·R(θ)ᵀ (reference quirk kept)
+      double P[9];
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) P[a * 3 + b] = Sg[(size_t)a * ld + b];
+      const double qo = L.q_obs;
+      const double GQG[4] = {(cs * qo) * cs + (-sn * qo) * (-sn), (cs * qo) * sn + (-sn * qo) * cs,
+                             (sn * qo) * cs + (cs * qo) * (-sn), (sn * qo) * sn + (cs * qo) * cs};
+      const int R = 2 * N2;
+      for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+        const int i = e / R, j = e - i * R;
+        if (i > j) continue;                       // upper + mirror keeps Σ exactly symmetric
+        const int oi = nw[i >> 1], oj = nw[j >> 1];
+        const double rxi = (double)xy[2 * oi], ryi = (double)xy[2 * oi + 1];
+        const double rxj = (double)xy[2 * oj], ryj = (double)xy[2 * oj + 1];
+        double gi[3], gj[3];
+        if ((i & 1) == 0) { gi[0] = 1; gi[1] = 0; gi[2] = -rxi * sn - ryi * cs; } else { gi[0] = 0; gi[1] = 1; gi[2] = rxi * cs - ryi * sn; }
+        if ((j & 1) == 0) { gj[0] = 1; gj[1] = 0; gj[2] = -rxj * sn - ryj * cs; } else { gj[0] = 0; gj[1] = 1; gj[2] = rxj * cs - ryj * sn; }
+        double acc = 0;
+        for (int b = 0; b < 3; ++b) {
+          double t = 0;
+          for (int a = 0; a < 3; ++a) t += gi[a] * P[a * 3 + b];
+          acc += t * gj[b];
+        }
+        const double v = acc + GQG[(i & 1) * 2 + (j & 1)];
+        Sg[(size_t)(n + i) * ld + n + j] = v;
+        Sg[(size_t)(n + j) * ld + n + i] = v;
+      }
+      // new means, rounded through float32 (:327-331, :341-342)
+      for (int q = threadIdx.x; q < N2; q += blockDim.x) {
+        const int i = nw[q];
+        const double ox = (double)xy[2 * i], oy = (double)xy[2 * i + 1];
+        mu[n + 2 * q] = (double)(float)(ox * cs - oy * sn + px);
+        mu[n + 2 * q + 1] = (double)(float)(ox * sn + oy * cs + py);
+      }
+    }
+  }
+  // last block of this session commits the new size and publishes the pose
+  __threadfence();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    st.N = N + N2;
+    if (overflow) st.flags |= FLAG_LANDMARK_CAPACITY;
+    st.ticket = 0;
+    if (in.pose_out) {
+      double *o = in.pose_out + (size_t)s * in.pose_ss + (size_t)t_idx * 3;
+      o[0] = mu[0]; o[1] = mu[1]; o[2] = mu[2];
+    }
+  }
+}
+
+// advances the replay step counter (own launch: every block of the step has read it by now)
+__global__ void k_advance_step(int *step) { *step += 1; }
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion at the C-ABI boundary (reference order ↔ internal slots)
+// ---------------------------------------------------------------------------------------------
+__device__ __host__ inline int ref_to_slot(int i) { return i < 3 ? i : i + 1; }
+
+// out: n_ref x n_ref column-major (ld_out), Eigen::MatrixXd layout
+__global__ void k_pack_sigma(Layout L, int s, double *out, int ld_out) {
+  const int n_ref = 3 + 2 * L.st[s].N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= n_ref || j >= n_ref) return;
+  const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  out[(size_t)j * ld_out + i] = Sg[(size_t)ref_to_slot(j) * L.ld + ref_to_slot(i)];
+}
+__global__ void k_pack_mu(Layout L, int s, double *out) {
+  const int n_ref = 3 + 2 * L.st[s].N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_ref) out[i] = L.mu[(size_t)s * L.ld + ref_to_slot(i)];
+}
+// landmark means and diagonal 2x2 blocks (row-major), what the node reads for markers / saving
+__global__ void k_pack_landmarks(Layout L, int s, double *xy, double *cov) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L.st[s].N) return;
+  const int a = kPoseSlots + 2 * j;
+  const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  const double *mu = L.mu + (size_t)s * L.ld;
+  xy[2 * j] = mu[a]; xy[2 * j + 1] = mu[a + 1];
+  cov[4 * j + 0] = Sg[(size_t)a * L.ld + a];       cov[4 * j + 1] = Sg[(size_t)a * L.ld + a + 1];
+  cov[4 * j + 2] = Sg[(size_t)(a + 1) * L.ld + a]; cov[4 * j + 3] = Sg[(size_t)(a + 1) * L.ld + a + 1];
+}
+// in: mu (n_ref), sigma n_ref x n_ref column-major (ld_in).  Symmetrised on the way in: (Σ+Σᵀ)/2.
+__global__ void k_unpack_state(Layout L, int s, const double *mu_in, const double *sig_in, int ld_in, int n_ref) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= n_ref || j >= n_ref) return;
+  double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  const double v = 0.5 * (sig_in[(size_t)j * ld_in + i] + sig_in[(size_t)i * ld_in + j]);
+  Sg[(size_t)ref_to_slot(i) * L.ld + ref_to_slot(j)] = v;
+  if (j == 0) L.mu[(size_t)s * L.ld + ref_to_slot(i)] = mu_in[i];
+}
+// PredictState (:97-152) into a packed copy: out_mu (n_ref), out_sigma column-major or nullptr
+__global__ void k_predict_state(Layout L, int s, double time, double *out_mu, double *out_sigma, int ld_out) {
+  const SessionState &st = L.st[s];
+  const int n_ref = 3 + 2 * st.N;
+  const double *mu = L.mu + (size_t)s * L.ld;
+  const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  const int ld = L.ld;
+  const double vt[3] = {st.vt[0], st.vt[1], st.vt[2]};
+  const MotionTerms t = motion_model(L, vt, mu[2], time - st.time);   // :100
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i >= n_ref || j >= n_ref) return;
+  if (j == 0) {
+    double v = mu[ref_to_slot(i)];
+    if (i < 2) v += t.d[i];
+    if (i == 2) v = wrap_angle(v + t.d[2]);
+    out_mu[i] = v;
+  }
+  if (!out_sigma) return;
+  const int a = ref_to_slot(i), b = ref_to_slot(j);
+  // (G Σ Gᵀ)[i][j] = Σ_ab G[i][a] Σ[a][b] G[j][b], G = I + g02·e0e2ᵀ + g12·e1e2ᵀ
+  const double gi = i == 0 ? t.g02 : (i == 1 ? t.g12 : 0.0);
+  const double gj = j == 0 ? t.g02 : (j == 1 ? t.g12 : 0.0);
+  double v = Sg[(size_t)a * ld + b];
+  if (i < 2) v += gi * Sg[(size_t)2 * ld + b];
+  if (j < 2) {
+    double col2 = Sg[(size_t)a * ld + 2];
+    if (i < 2) col2 += gi * Sg[(size_t)2 * ld + 2];
+    v += gj * col2;
+  }
+  if (i < 3 && j < 3) v += t.V[i * 3 + j];
+  out_sigma[(size_t)j * ld_out + i] = v;
+}
+
+}  // namespace rekf
