@@ -142,6 +142,8 @@ REKF_API int rekf_time(rekf_handle *h, int session, double *time_out);
 REKF_API int rekf_get_mu(rekf_handle *h, int session, double *mu, int cap, int *n_out);
 /* pose + its 3x3 covariance block (what ros_node.cc:802-817 publishes); cov33 column-major. */
 REKF_API int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]);
+/* poses of all sessions in one read: S x 3 doubles (the per-step result of a batched replay) */
+REKF_API int rekf_batch_get_pose(rekf_handle *h, double *poses);
 /* landmark means + diagonal 2x2 blocks (what ros_node.cc:97-136,739-765 reads); cov row-major
  * (0,0),(0,1),(1,0),(1,1) per landmark like the save format. */
 REKF_API int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, int cap,

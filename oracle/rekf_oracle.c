@@ -72,6 +72,34 @@ static void pack_b(const double *B, int ldb, int trans, int k0, int j0, int kc, 
   }
 }
 
+#ifndef __AVX__
+/* Baseline x86-64 (SSE2, what the reference's flag-less Release build targets): 16-byte vectors, the
+ * 8x4 block as two 4x4 halves so the eight accumulators stay in the sixteen xmm registers. */
+typedef double v2d __attribute__((vector_size(16), aligned(8)));
+static inline void micro_kernel(int kc, const double *Ap, const double *Bp, double *acc /*MR*NR col-major*/) {
+  for (int half = 0; half < 2; ++half) {
+    const double *a = Ap + 4 * half, *b = Bp;
+    v2d c00 = {0, 0}, c10 = c00, c01 = c00, c11 = c00, c02 = c00, c12 = c00, c03 = c00, c13 = c00;
+    for (int k = 0; k < kc; ++k) {
+      v2d a0, a1;
+      memcpy(&a0, a, 16);
+      memcpy(&a1, a + 2, 16);
+      const v2d b0 = {b[0], b[0]}, b1 = {b[1], b[1]}, b2 = {b[2], b[2]}, b3 = {b[3], b[3]};
+      c00 += a0 * b0; c10 += a1 * b0;
+      c01 += a0 * b1; c11 += a1 * b1;
+      c02 += a0 * b2; c12 += a1 * b2;
+      c03 += a0 * b3; c13 += a1 * b3;
+      a += MR;
+      b += NR;
+    }
+    double *o = acc + 4 * half;
+    memcpy(o + 0, &c00, 16);  memcpy(o + 2, &c10, 16);
+    memcpy(o + 8, &c01, 16);  memcpy(o + 10, &c11, 16);
+    memcpy(o + 16, &c02, 16); memcpy(o + 18, &c12, 16);
+    memcpy(o + 24, &c03, 16); memcpy(o + 26, &c13, 16);
+  }
+}
+#else
 static inline void micro_kernel(int kc, const double *Ap, const double *Bp, double *acc /*MR*NR col-major*/) {
   v4d c00 = {0, 0, 0, 0}, c10 = c00, c01 = c00, c11 = c00, c02 = c00, c12 = c00, c03 = c00, c13 = c00;
   for (int k = 0; k < kc; ++k) {
@@ -91,6 +119,7 @@ static inline void micro_kernel(int kc, const double *Ap, const double *Bp, doub
   memcpy(acc + 16, &c02, 32); memcpy(acc + 20, &c12, 32);
   memcpy(acc + 24, &c03, 32); memcpy(acc + 28, &c13, 32);
 }
+#endif
 
 /* C = op(A) op(B); the stand-in for Eigen's GEBP product kernel (blocked, packed, vectorised) */
 void oracle_dgemm(int transA, int transB, int M, int N, int K, const double *A, int lda,

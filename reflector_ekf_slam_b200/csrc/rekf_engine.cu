@@ -581,6 +581,15 @@ int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) 
   return REKF_OK;
 }
 
+int rekf_batch_get_pose(rekf_handle *h, double *poses) {
+  if (!h || !poses) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  CK(cudaMemcpy2DAsync(poses, sizeof(double) * 3, L.mu, sizeof(double) * L.ld, sizeof(double) * 3, L.S,
+                       cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
 int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, int cap, int *count_out) {
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;

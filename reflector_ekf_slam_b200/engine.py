@@ -24,7 +24,7 @@ ABI_SYMBOLS = [
     "rekf_default_options", "rekf_create", "rekf_create_batch", "rekf_destroy", "rekf_last_error", "rekf_version",
     "rekf_sessions", "rekf_handle_odometry", "rekf_handle_observation", "rekf_handle_imu",
     "rekf_batch_handle_odometry", "rekf_batch_handle_observation", "rekf_replay_device", "rekf_dim", "rekf_time",
-    "rekf_get_mu", "rekf_get_pose", "rekf_get_landmarks", "rekf_get_sigma", "rekf_get_match_result",
+    "rekf_get_mu", "rekf_get_pose", "rekf_batch_get_pose", "rekf_get_landmarks", "rekf_get_sigma", "rekf_get_match_result",
     "rekf_predict_state", "rekf_set_state", "rekf_set_map", "rekf_get_map", "rekf_load_map_txt", "rekf_save_map_txt",
     "rekf_sync", "rekf_stream", "rekf_timer_start", "rekf_timer_stop", "rekf_profile_enable", "rekf_profile_read",
     "rekf_launch_count", "rekf_device_error_flags",
@@ -66,6 +66,7 @@ def load_library(path=None):
         "rekf_time": (i, [vp, i, P(d)]),
         "rekf_get_mu": (i, [vp, i, vp, i, P(i)]),
         "rekf_get_pose": (i, [vp, i, vp, vp]),
+        "rekf_batch_get_pose": (i, [vp, vp]),
         "rekf_get_landmarks": (i, [vp, i, vp, vp, i, P(i)]),
         "rekf_get_sigma": (i, [vp, i, vp, i]),
         "rekf_get_match_result": (i, [vp, i, vp, P(i), vp, P(i), vp, P(i), i]),
@@ -172,6 +173,12 @@ class EKFBatch:
         c = np.zeros((3, 3)) if with_cov else None
         self._ck(self.lib.rekf_get_pose(self.h, s, _ptr(p), _ptr(c)))
         return (p, c) if with_cov else p
+
+    def poses(self, out=None):
+        """(S, 3) poses of all sessions in one device→host read."""
+        out = np.zeros((self.S, 3)) if out is None else out
+        self._ck(self.lib.rekf_batch_get_pose(self.h, _ptr(out)))
+        return out
 
     def landmarks(self, s=0):
         cnt = C.c_int()

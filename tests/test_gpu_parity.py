@@ -115,7 +115,8 @@ def test_negative_dt_stale_odometry_empty_frames(engine_lib):
     compare_state(ekf, orc)
     assert ekf.GetLatestTime() == orc.GetLatestTime() == 1.2
     S = ekf.GetCoviarance()
-    assert abs(S[3, 5] - orc.GetCoviarance()[3, 5]) < 1e-15 and S[3, 5] != 0.0
+    So = orc.GetCoviarance()
+    assert abs(S[3, 5] - So[3, 5]) < 1e-5 * abs(So[3, 5]) and S[3, 5] != 0.0    # same-frame +Qt cross block (:354)
 
 
 def test_capacity_flags(engine_lib):
