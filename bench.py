@@ -39,7 +39,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--sessions", type=int, default=8, help="independent sessions per GPU")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cov", default="tcgen05", choices=["tcgen05", "f64"])
+    ap.add_argument("--cov", default="i8", choices=["i8", "tcgen05", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=25.0)
     ap.add_argument("--single-session", action="store_true", help="also time one session alone (latency-bound figure)")
@@ -213,7 +213,7 @@ def run_b200(args):
     S, K, W = args.sessions, args.steps, args.warmup
     T = W + K
     EXTRA = min(K, 50) + min(K, 100)          # profiling pass + end-to-end pass
-    cov = {"tcgen05": 0, "f64": 1}[args.cov]
+    cov = {"tcgen05": 0, "f64": 1, "i8": 2}[args.cov]
 
     # ---- inputs: rank 0 generates every session's stream, NCCL scatters the packed shards ----------
     streams = None
@@ -290,7 +290,7 @@ def run_b200(args):
     prof = batch.profile_read()
     batch.profile_enable(False)
     step_us = sum(v[0] for v in prof.values())
-    syrk_name = "k_syrk_tcgen05" if cov == 0 else "k_syrk_f64"
+    syrk_name = {0: "k_syrk_tcgen05", 1: "k_syrk_f64", 2: "k_syrk_tcgen05_i8"}[cov]
     syrk_us = prof[syrk_name][0]
     n_ref, r = 3 + 2 * N_LM, 2 * M_OBS
     hbm_peak, bf16_peak, peak_kind = measured_peaks()
@@ -363,7 +363,8 @@ def run_b200(args):
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 state/solve + tf32x3 tcgen05 covariance GEMM (fp32 TMEM accumulate)" if cov == 0 else "f64",
+            "dtype": {0: "f64 state/solve + tf32x3 tcgen05 covariance GEMM (fp32 TMEM accumulate)", 1: "f64",
+                      2: "f64 state/solve + exact int8-slice (4x7-bit) tcgen05 covariance GEMM (s32 TMEM accumulate)"}[cov],
             "data": "synthetic",
             "config": {"workload": f"{CONFIG}: synthetic 2D stream, N={N_LM} landmarks, {M_OBS} observed/step, diff odom; "
                                    f"{S} independent sessions per GPU in lock-step (BASELINE config 5 per-GPU slice)",

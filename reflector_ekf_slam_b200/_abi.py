@@ -9,6 +9,7 @@ REKF_ODOM_OMNI = 1
 
 REKF_COV_TCGEN05_TF32X3 = 0
 REKF_COV_SIMT_F64 = 1
+REKF_COV_TCGEN05_I8X4 = 2
 
 REKF_MAP_LOADER_FIXED = 0
 REKF_MAP_LOADER_REFERENCE = 1

@@ -90,6 +90,9 @@ struct Layout {
   double *Dinv;   // [S][rld/32][32][32] inverses of L's diagonal blocks
   float *Wt_hi, *Wt_lo;  // [S][ld][rld] tf32 hi/lo split of Wᵀ (K-major operands of the tcgen05 SYRK)
   double *W64;    // [S][ld][rld] fp64 Wᵀ (REKF_COV_SIMT_F64 only, else nullptr)
+  int8_t *Wq;     // [S][4][ld][kq] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4)
+  int *Wexp;      // [S][ld] per-row power-of-two scale e_c of Wq
+  int kq;         // round_up(rcap, 64): K extent of Wq in bytes
   int *step;      // device step counter for replay
 };
 

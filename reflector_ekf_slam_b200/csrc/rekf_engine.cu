@@ -18,6 +18,7 @@
 #include "rekf_device.cuh"
 #include "rekf_kernels.cuh"
 #include "syrk_tcgen05.cuh"
+#include "syrk_tcgen05_i8.cuh"
 
 using namespace rekf;
 
@@ -65,6 +66,7 @@ struct rekf_handle {
   InputRef graph_in{};
   // tcgen05 SYRK resources
   SyrkTc tc{};
+  SyrkI8 tc8{};
   std::vector<void *> allocations;
 };
 
@@ -183,6 +185,9 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
     ProfScope p(h, K_SYRK);
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
       k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);
+    } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
+      int rc = syrk_i8_launch(h->tc8, L, h->stream);
+      if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
       int rc = syrk_tc_launch(h->tc, L, h->stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -290,6 +295,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   L.rcap = 2 * L.mcap + 4;
   L.rld = round_up(L.rcap, kKBlock);
   L.sld = L.rld + 8;
+  L.kq = round_up(L.rcap, 64);
   L.odom_model = opts->odom_model == REKF_ODOM_DIFF ? 0 : 1;   // :13-32: everything but DIFF is the 3x3 model
   L.q_lin = opts->linear_velocity_cov;
   L.q_ang = opts->angular_velocity_cov;
@@ -317,6 +323,9 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   } else if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
     if ((rc = dev_alloc(h, &L.Wt_hi, S * L.ld * L.rld))) return rc;
     if ((rc = dev_alloc(h, &L.Wt_lo, S * L.ld * L.rld))) return rc;
+  } else if (opts->cov_update == REKF_COV_TCGEN05_I8X4) {
+    if ((rc = dev_alloc(h, &L.Wq, S * 4 * L.ld * L.kq))) return rc;
+    if ((rc = dev_alloc(h, &L.Wexp, S * L.ld))) return rc;
   } else {
     return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown cov_update %d", opts->cov_update);
   }
@@ -369,6 +378,10 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
     const char *why = syrk_tc_init(h->tc, L);
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK setup failed: %s", why);
+  }
+  if (opts->cov_update == REKF_COV_TCGEN05_I8X4) {
+    const char *why = syrk_i8_init(h->tc8, L);
+    if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK setup failed: %s", why);
   }
   if (opts->map_path && opts->map_path[0]) rekf_load_map_txt(h, opts->map_path);   // :36
   CK(cudaStreamSynchronize(h->stream));
@@ -819,7 +832,8 @@ int rekf_profile_read(rekf_handle *h, const char **names, double *mean_us, int *
   drain_profile(h);
   int c = 0;
   for (int k = 0; k < K_COUNT && c < cap; ++k) {
-    if (names) names[c] = (k == K_SYRK && h->opts.cov_update == REKF_COV_TCGEN05_TF32X3) ? "k_syrk_tcgen05" : (k == K_SYRK ? "k_syrk_f64" : kKernelNames[k]);
+    static const char *syrk_names[3] = {"k_syrk_tcgen05", "k_syrk_f64", "k_syrk_tcgen05_i8"};
+    if (names) names[c] = (k == K_SYRK) ? syrk_names[h->opts.cov_update] : kKernelNames[k];
     if (mean_us) mean_us[c] = h->prof_calls[k] ? h->prof_us[k] / h->prof_calls[k] : 0.0;
     if (calls) calls[c] = h->prof_calls[k];
     ++c;

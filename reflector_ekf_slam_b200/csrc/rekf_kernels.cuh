@@ -588,7 +588,40 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
     }
   }
   // Wᵀ panels (row c, K contiguous), zero beyond r
-  if (L.W64) {
+  if (L.Wq) {
+    // exact int8 digit slices for the kind::i8 SYRK: x = w·2^-e, |x| <= 1/2, x ≈ Σ_p d_p·2^(-7(p+1))
+    __shared__ int sexp[kWCols];
+    for (int cc = warp; cc < kWCols; cc += 8) {
+      double mx = 0.0;
+      for (int k = lane; k < r; k += 32) mx = fmax(mx, fabs(Y[k * kYS + cc]));
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+      const int e = (mx > 0.0 && c0 + cc < n) ? ilogb(mx) + 2 : 0;
+      if (lane == 0) { sexp[cc] = e; L.Wexp[(size_t)s * ld + c0 + cc] = e; }
+    }
+    __syncthreads();
+    const int kq4 = L.kq / 4;
+    for (int e4 = tid; e4 < kWCols * kq4; e4 += blockDim.x) {
+      const int cc = e4 / kq4, k0 = (e4 - cc * kq4) * 4;
+      const int e = sexp[cc];
+      const bool live = (c0 + cc < n);
+      uint32_t packed[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + u;
+        double rem = (live && k < r) ? scalbn(Y[k * kYS + cc], 7 - e) : 0.0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const double d = rint(rem);
+          packed[p] |= ((uint32_t)(int)d & 0xffu) << (8 * u);
+          rem = (rem - d) * 128.0;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        *reinterpret_cast<uint32_t *>(L.Wq + (((size_t)s * 4 + p) * ld + c0 + cc) * L.kq + k0) = packed[p];
+    }
+  } else if (L.W64) {
     double *W = L.W64 + (size_t)s * ld * rld;
     for (int e = tid; e < kWCols * rld; e += blockDim.x) {
       const int cc = e / rld, k = e - cc * rld;

@@ -19,7 +19,7 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 every = int(sys.argv[3]) if len(sys.argv) > 3 else 50
 st = make_stream(cfg, steps)
 engines = {name: ReflectorEKFSLAM(odom_model=st["model"], max_landmarks=st["N"], max_observations=st["m"], cov_update=mode)
-           for name, mode in (("tcgen05", 0), ("f64", 1))}
+           for name, mode in (("tf32x3", 0), ("f64", 1), ("i8x4", 2))}
 orc = Oracle(algebra=STRUCTURED, odom_model=st["model"], native=True)
 t0 = time.time()
 for k in range(len(st["odom"])):

@@ -10,7 +10,7 @@ from helpers import MU_TOL_M, SIGMA_REL_FRO, compare_matches, compare_state, dri
 
 pytestmark = pytest.mark.gpu
 
-COV_MODES = {"tcgen05": 0, "f64": 1}
+COV_MODES = {"tcgen05": 0, "f64": 1, "i8": 2}
 
 
 def _make(cfg_stream, cov, **kw):
@@ -24,7 +24,7 @@ def _make(cfg_stream, cov, **kw):
     return ekf, orc
 
 
-@pytest.mark.parametrize("cov", ["f64", "tcgen05"])
+@pytest.mark.parametrize("cov", ["f64", "tcgen05", "i8"])
 @pytest.mark.parametrize("cfg,steps", [("T0", 40), ("T1", 30)])
 def test_small_streams_every_step(engine_lib, cfg, steps, cov):
     from reflector_ekf_slam_b200.synth import make_stream
@@ -42,7 +42,7 @@ def test_small_streams_every_step(engine_lib, cfg, steps, cov):
     print(f"{cfg}/{cov}: worst |dmu| {worst[0]:.2e} m, worst rel-Fro {worst[1]:.2e}")
 
 
-@pytest.mark.parametrize("cov", ["f64", "tcgen05"])
+@pytest.mark.parametrize("cov", ["f64", "tcgen05", "i8"])
 def test_c2_stream(engine_lib, cov):
     """Config C2 (N=256, m=50): map building + 40 steady steps, Σ compared every 5th step."""
     from reflector_ekf_slam_b200.synth import make_stream
@@ -59,7 +59,7 @@ def test_c2_stream(engine_lib, cov):
     print(f"C2/{cov}: worst |dmu| {worst[0]:.2e} m, worst rel-Fro {worst[1]:.2e}")
 
 
-@pytest.mark.parametrize("cov", ["f64", "tcgen05"])
+@pytest.mark.parametrize("cov", ["f64", "tcgen05", "i8"])
 def test_c3_warm_start_and_steps(engine_lib, cov):
     """Config C3 (N=1024, m=100, the headline size): the oracle builds the map, the snapshot is injected
     with rekf_set_state, then 6 steady steps are compared."""
