@@ -58,10 +58,11 @@ enum { REKF_ODOM_DIFF = 0, REKF_ODOM_OMNI = 1 };
 
 /* How Sigma <- Sigma - K H Sigma (reflector_ekf_slam.cc:308) is evaluated on the device. */
 enum {
-  REKF_COV_TCGEN05_TF32X3 = 0,   /* tcgen05.mma kind::tf32, 3-term split, fp32 TMEM accumulate (default) */
+  REKF_COV_TCGEN05_TF32X3 = 0,   /* tcgen05.mma kind::tf32, 3-term split, fp32 TMEM accumulate (fp32-class: drifts) */
   REKF_COV_SIMT_F64 = 1,         /* fp64 CUDA-core SYRK (reference-accuracy mode) */
   REKF_COV_TCGEN05_I8X4 = 2      /* tcgen05.mma kind::i8 over four exact 7-bit digit slices, s32 TMEM accumulate:
-                                    integer-exact products, ~1e-8 relative truncation (fp64-class, tensor-core speed) */
+                                    integer-exact products; frames whose downdate cancels deeply are routed to the
+                                    fp64 SYRK on the device.  DEFAULT. */
 };
 
 /* Loader for the 2-line landmark map file (reflector_ekf_slam.cc:43-95). */

@@ -59,7 +59,7 @@ def make_options(
     max_observations=0,
     max_map_landmarks=0,
     device=0,
-    cov_update=REKF_COV_TCGEN05_TF32X3,
+    cov_update=REKF_COV_TCGEN05_I8X4,
     map_loader=REKF_MAP_LOADER_FIXED,
     stream=None,
     use_graphs=0,

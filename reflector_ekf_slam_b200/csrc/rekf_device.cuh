@@ -23,6 +23,8 @@ constexpr int kSigmaTile = 128;   // Σ pitch granularity = tcgen05 output tile 
 constexpr int kKBlock = 32;       // measurement-row (GEMM K) granularity: one 128-byte swizzle row of tf32
 constexpr int kCholNb = 32;       // Cholesky / TRSM block size
 constexpr int kWCols = 16;        // columns of W = L⁻¹·H·Σ solved per CTA
+// int8 SYRK admission: (row scale)² / posterior variance above this sends the frame to the fp64 SYRK
+constexpr double kMaxSliceGain2 = 1.0;
 
 enum : int {
   FLAG_LANDMARK_CAPACITY = 1,     // augmentation would exceed max_landmarks: extra reflectors dropped
@@ -43,6 +45,7 @@ struct SessionState {
   int r;                // measurement rows of this frame: 2(M+Mmap) (+3 with a GPS pose), 0 = no update
   int flags;            // sticky FLAG_* bits
   unsigned ticket;      // last-block-done counter (augment kernel)
+  int exact_update;     // this frame's downdate cancels too deeply for the int8 slices: use the fp64 SYRK
 };
 
 // Where the current message comes from: the handle's device mailbox (host path) or device-resident
@@ -93,6 +96,7 @@ struct Layout {
   int8_t *Wq;     // [S][4][ld][kq] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4)
   int *Wexp;      // [S][ld] per-row power-of-two scale e_c of Wq
   int kq;         // round_up(rcap, 64): K extent of Wq in bytes
+  double *Wdiag;  // [S][ld] exact fp64 diagonal of Wᵀ·W (tensor-core modes use it for Σ[i][i])
   int *step;      // device step counter for replay
 };
 

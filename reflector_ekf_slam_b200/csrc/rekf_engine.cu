@@ -186,6 +186,7 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
       k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
+      k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);   // exits unless st.exact_update
       int rc = syrk_i8_launch(h->tc8, L, h->stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -253,7 +254,7 @@ void rekf_default_options(rekf_options *o) {
   o->max_landmarks = 1024;
   o->max_observations = 128;
   o->max_map_landmarks = 1024;
-  o->cov_update = REKF_COV_TCGEN05_TF32X3;
+  o->cov_update = REKF_COV_TCGEN05_I8X4;
   o->map_loader = REKF_MAP_LOADER_FIXED;
 }
 
@@ -325,10 +326,12 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     if ((rc = dev_alloc(h, &L.Wt_lo, S * L.ld * L.rld))) return rc;
   } else if (opts->cov_update == REKF_COV_TCGEN05_I8X4) {
     if ((rc = dev_alloc(h, &L.Wq, S * 4 * L.ld * L.kq))) return rc;
+    if ((rc = dev_alloc(h, &L.W64, S * L.ld * L.rld))) return rc;
     if ((rc = dev_alloc(h, &L.Wexp, S * L.ld))) return rc;
   } else {
     return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown cov_update %d", opts->cov_update);
   }
+  if (opts->cov_update != REKF_COV_SIMT_F64 && (rc = dev_alloc(h, &L.Wdiag, S * L.ld))) return rc;
   if ((rc = dev_alloc(h, &L.step, 1))) return rc;
 
   // initial state: time, pose (:8-11)

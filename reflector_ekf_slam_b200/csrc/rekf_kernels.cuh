@@ -306,6 +306,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     st.m = m; st.M = M; st.Mmap = Mm; st.N2 = N2; st.r = r;
     st.flags = flags0 | flag_add;
     st.ticket = 0;
+    st.exact_update = 0;
   }
 }
 
@@ -579,15 +580,33 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
   for (int cc = warp; cc < kWCols; cc += 8) {
     const int c = c0 + cc;
     double a = 0.0;
-    for (int k = lane; k < r; k += 32) a = fma(Y[k * kYS + cc], Sb[(size_t)k * sld + r], a);
+    double d2 = 0.0;
+    for (int k = lane; k < r; k += 32) {
+      const double w = Y[k * kYS + cc];
+      a = fma(w, Sb[(size_t)k * sld + r], a);
+      d2 = fma(w, w, d2);
+    }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xffffffffu, a, off);
+    for (int off = 16; off > 0; off >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      d2 += __shfl_xor_sync(0xffffffffu, d2, off);
+    }
     if (lane == 0 && c < n) {
       const double v = mu[c] + a;
       mu[c] = (c == 2) ? wrap_angle(v) : v;
     }
+    // The diagonal of the downdate is a sum of squares: every rounding/truncation of the tensor-core
+    // product has the same sign there and would accumulate step after step, so it is kept in fp64.
+    if (lane == 0 && L.Wdiag) L.Wdiag[(size_t)s * ld + c] = (c < n) ? d2 : 0.0;
   }
   // Wᵀ panels (row c, K contiguous), zero beyond r
+  if (L.W64) {
+    double *W = L.W64 + (size_t)s * ld * rld;
+    for (int e = tid; e < kWCols * rld; e += blockDim.x) {
+      const int cc = e / rld, k = e - cc * rld;
+      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kYS + cc] : 0.0;
+    }
+  }
   if (L.Wq) {
     // exact int8 digit slices for the kind::i8 SYRK: x = w·2^-e, |x| <= 1/2, x ≈ Σ_p d_p·2^(-7(p+1))
     __shared__ int sexp[kWCols];
@@ -597,7 +616,17 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
       const int e = (mx > 0.0 && c0 + cc < n) ? ilogb(mx) + 2 : 0;
-      if (lane == 0) { sexp[cc] = e; L.Wexp[(size_t)s * ld + c0 + cc] = e; }
+      if (lane == 0) {
+        sexp[cc] = e; L.Wexp[(size_t)s * ld + c0 + cc] = e;
+        // The slices resolve 2^-29 of the row scale 2^e.  When the downdate removes almost all of a
+        // state's variance (first update after dead reckoning, loop closure) that is no longer small
+        // against the posterior: such frames take the fp64 SYRK instead.
+        if (mx > 0.0 && c0 + cc < n) {
+          const int c = c0 + cc;
+          const double post = Sg[(size_t)c * ld + c] - L.Wdiag[(size_t)s * ld + c];
+          if (!(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post) atomicOr(&L.st[s].exact_update, 1);
+        }
+      }
     }
     __syncthreads();
     const int kq4 = L.kq / 4;
@@ -621,13 +650,7 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
       for (int p = 0; p < 4; ++p)
         *reinterpret_cast<uint32_t *>(L.Wq + (((size_t)s * 4 + p) * ld + c0 + cc) * L.kq + k0) = packed[p];
     }
-  } else if (L.W64) {
-    double *W = L.W64 + (size_t)s * ld * rld;
-    for (int e = tid; e < kWCols * rld; e += blockDim.x) {
-      const int cc = e / rld, k = e - cc * rld;
-      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kYS + cc] : 0.0;
-    }
-  } else {
+  } else if (L.Wt_hi) {
     float *Wh = L.Wt_hi + (size_t)s * ld * rld, *Wl = L.Wt_lo + (size_t)s * ld * rld;
     for (int e = tid; e < kWCols * rld; e += blockDim.x) {
       const int cc = e / rld, k = e - cc * rld;
@@ -649,6 +672,7 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
   const int r = st.r;
   const int ti = blockIdx.y, tj = blockIdx.x;
   if (r == 0 || ti > tj) return;
+  if (L.Wq && !st.exact_update) return;     // int8 tensor-core SYRK handles this frame
   const int n = internal_dim(st.N);
   const int i0 = ti * 64, j0 = tj * 64;
   if (j0 >= n) return;

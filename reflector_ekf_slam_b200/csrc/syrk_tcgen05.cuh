@@ -215,6 +215,14 @@ k_syrk_tcgen05(Layout L, const __grid_constant__ CUtensorMap map_hi, const __gri
 #pragma unroll
         for (int u = 0; u < 16; ++u)
           cur[u] -= (double)__uint_as_float(vm[u]) + (double)__uint_as_float(vc[u]);
+        if (diag) {
+          const int u = i - jbase;                      // diagonal element: exact fp64 sum of squares from k_solve_w
+          if (u >= 0 && u < 16) {
+            const double dd = L.Wdiag[(size_t)s * ld + i];
+#pragma unroll
+            for (int v = 0; v < 16; ++v) if (v == u) cur[v] = row[v] - dd;
+          }
+        }
         if (!diag && jbase + 15 < n) {
 #pragma unroll
           for (int u = 0; u < 16; u += 2) *reinterpret_cast<double2 *>(row + u) = make_double2(cur[u], cur[u + 1]);

@@ -67,7 +67,7 @@ k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map) {
   const int s = blockIdx.y;
   SessionState &st = L.st[s];
   const int r = st.r;
-  if (r == 0) return;
+  if (r == 0 || st.exact_update) return;   // deep-cancellation frames go to k_syrk_f64
   const int n = internal_dim(st.N);
   int tj = (int)((sqrtf(8.0f * (float)blockIdx.x + 1.0f) - 1.0f) * 0.5f);
   while ((tj + 1) * (tj + 2) / 2 <= (int)blockIdx.x) ++tj;
@@ -184,6 +184,14 @@ k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map) {
           const double v = (double)(int)g0[u] * 0x1p-14 + (double)(int)g1[u] * 0x1p-21 + (double)(int)g2[u] * 0x1p-28 +
                            (double)(int)g3[u] * 0x1p-35;
           cur[u] -= scalbn(v, ei + We[min(jbase + u, ld - 1)]);
+        }
+        if (diag) {
+          const int u = i - jbase;                      // diagonal element: exact fp64 sum of squares from k_solve_w
+          if (u >= 0 && u < 16) {
+            const double dd = L.Wdiag[(size_t)s * ld + i];
+#pragma unroll
+            for (int v = 0; v < 16; ++v) if (v == u) cur[v] = row[v] - dd;
+          }
         }
         if (!diag && jbase + 15 < n) {
 #pragma unroll

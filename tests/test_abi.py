@@ -32,7 +32,7 @@ def test_options_struct_layout_matches_header(engine_lib):
     assert abs(o.linear_velocity_cov - 0.0025) < 1e-18 and abs(o.angular_velocity_cov - 0.0064) < 1e-18
     assert abs(o.observation_cov - 0.0025) < 1e-18
     assert (o.max_landmarks, o.max_observations, o.max_map_landmarks) == (1024, 128, 1024)
-    assert o.cov_update == 0 and o.map_loader == 0 and not o.stream and o.use_graphs == 0
+    assert o.cov_update == 2 and o.map_loader == 0 and not o.stream and o.use_graphs == 0
     assert engine_lib.rekf_version().startswith(b"rekf-b200")
 
 

@@ -88,12 +88,13 @@ def test_c3_warm_start_and_steps(engine_lib, cov):
 def test_covariance_stays_exactly_symmetric_and_psd(engine_lib):
     from reflector_ekf_slam_b200.synth import make_stream
     st = make_stream("T1", 20)
-    ekf, _ = _make(st, "tcgen05")
-    for k in range(len(st["odom"])):
-        drive_engine(ekf, st, k)
-    S = ekf.GetCoviarance()
-    assert np.array_equal(S, S.T)
-    assert np.linalg.eigvalsh(S).min() > -1e-9
+    for cov, floor in (("i8", -1e-9), ("f64", -1e-12), ("tcgen05", -1e-7)):
+        ekf, _ = _make(st, cov)
+        for k in range(len(st["odom"])):
+            drive_engine(ekf, st, k)
+        S = ekf.GetCoviarance()
+        assert np.array_equal(S, S.T), cov            # bit-exact symmetry in every mode
+        assert np.linalg.eigvalsh(S).min() > floor, cov
 
 
 def test_negative_dt_stale_odometry_empty_frames(engine_lib):
