@@ -17,6 +17,8 @@
 #include "../../include/rekf.h"
 #include "rekf_device.cuh"
 #include "rekf_kernels.cuh"
+#include "chol_smem.cuh"
+#include "solve_w.cuh"
 #include "syrk_tcgen05.cuh"
 #include "syrk_tcgen05_i8.cuh"
 
@@ -65,6 +67,7 @@ struct rekf_handle {
   cudaGraphExec_t step_graph = nullptr;
   InputRef graph_in{};
   // tcgen05 SYRK resources
+  bool chol_resident = false, solve_w2 = false;
   SyrkTc tc{};
   SyrkI8 tc8{};
   std::vector<void *> allocations;
@@ -150,7 +153,7 @@ void drain_profile(rekf_handle *h) {
   h->prof.clear();
 }
 
-size_t smem_front(const Layout &L) { return sizeof(int) * 2 * (size_t)L.mcap; }
+size_t smem_front(const Layout &L) { return sizeof(int) * 2 * (size_t)L.mcap + sizeof(float2) * (size_t)L.Ncap; }
 size_t smem_chol(const Layout &L) { return sizeof(double) * ((size_t)(L.rcap + 1) * kPS + (size_t)kCholNb * kPS); }
 size_t smem_solve(const Layout &L) { return sizeof(double) * (size_t)L.rld * kYS; }
 
@@ -175,11 +178,13 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
   }
   {
     ProfScope p(h, K_CHOL);
-    k_cholesky<<<L.S, 1024, smem_chol(L), h->stream>>>(L);
+    if (h->chol_resident) k_cholesky_smem<<<L.S, kCholSmemThreads, smem_chol_resident(L.rcap), h->stream>>>(L);
+    else k_cholesky<<<L.S, 1024, smem_chol(L), h->stream>>>(L);
   }
   {
     ProfScope p(h, K_SOLVE);
-    k_solve_w<<<dim3(L.ld / kWCols, 1, L.S), 256, smem_solve(L), h->stream>>>(L);
+    if (h->solve_w2) k_solve_w2<<<dim3(L.ld / kW2Cols, 1, L.S), 256, smem_solve_w2(L.rld), h->stream>>>(L);
+    else k_solve_w<<<dim3(L.ld / kWCols, 1, L.S), 256, smem_solve(L), h->stream>>>(L);
   }
   {
     ProfScope p(h, K_SYRK);
@@ -375,7 +380,14 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   CK(cudaEventCreate(&h->t0));
   CK(cudaEventCreate(&h->t1));
   // opt in to large dynamic shared memory where needed
+  if (smem_front(L) > 200 * 1024) return fail(h, REKF_ERR_CAPACITY, "max_landmarks %d needs %zu B of shared memory in k_observation_front", L.Ncap, smem_front(L));
+  CK(cudaFuncSetAttribute(k_observation_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_front(L)));
   CK(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol(L)));
+  h->solve_w2 = smem_solve_w2(L.rld) <= 227 * 1024;
+  if (h->solve_w2) CK(cudaFuncSetAttribute(k_solve_w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w2(L.rld)));
+  h->chol_resident = smem_chol_resident(L.rcap) <= 227 * 1024;
+  if (h->chol_resident)
+    CK(cudaFuncSetAttribute(k_cholesky_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(L.rcap)));
   CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
   if (smem_chol(L) > 227 * 1024) return fail(h, REKF_ERR_CAPACITY, "max_observations %d needs %zu B of shared memory in k_cholesky", L.mcap, smem_chol(L));
   if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {

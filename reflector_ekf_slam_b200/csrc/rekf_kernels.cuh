@@ -177,8 +177,15 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
 
   int *kind = sm_i;                 // [mcap]
   int *target = sm_i + L.mcap;      // [mcap]
+  // landmark means rounded to float32 once per frame (:431 does it per pair; F2F.F32.F64 is a slow-pipe op)
+  float2 *lmf = reinterpret_cast<float2 *>(sm_i + 2 * L.mcap);   // [Ncap]
   const double *mu = L.mu + (size_t)s * L.ld;
   const int N = st.N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const double2 l = *reinterpret_cast<const double2 *>(mu + kPoseSlots + 2 * j);
+    lmf[j] = make_float2((float)l.x, (float)l.y);
+  }
+  __syncthreads();
   const int Mmap = *L.map_count;
   const double px = mu[0], py = mu[1], th = mu[2];
   double sn, cs;
@@ -209,15 +216,17 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     if (k == kMatchNew && N > 0) {                 // :426-451
       double best = INFINITY;
       int bj = 0x7fffffff;
+      // Compare squared distances (dx², dy² are exact in fp64, so d² orders exactly like the reference's
+      // sqrt(d²) except where two sqrt results round to the same double); sqrt only for the gate.
       for (int j = lane; j < N; j += 32) {
-        const double2 l = *reinterpret_cast<const double2 *>(mu + kPoseSlots + 2 * j);
-        const float dfx = gx - (float)l.x, dfy = gy - (float)l.y;                  // :431, :433
+        const float2 l = lmf[j];
+        const float dfx = gx - l.x, dfy = gy - l.y;                                // :431, :433
         const double dx = (double)dfx, dy = (double)dfy;
-        const double dist = sqrt(dx * dx + dy * dy);                               // :437 Euclidean
-        if (dist < best) { best = dist; bj = j; }
+        const double d2 = dx * dx + dy * dy;                                       // :437 Euclidean
+        if (d2 < best) { best = d2; bj = j; }
       }
       warp_argmin(best, bj);
-      if (best < 0.6) { k = kMatchState; tgt = bj; }                               // :446
+      if (sqrt(best) < 0.6) { k = kMatchState; tgt = bj; }                         // :446
     }
     if (lane == 0) { kind[i] = k; target[i] = tgt; }
   }
