@@ -190,6 +190,10 @@ REKF_API int rekf_profile_read(rekf_handle *h, const char **names, double *mean_
 REKF_API int64_t rekf_launch_count(const rekf_handle *h);
 /* raw device pointers for tests / profiling (Sigma is stored in the engine's internal layout) */
 REKF_API int rekf_device_error_flags(rekf_handle *h, int session, int *flags_out);
+/* Raw copy of a named internal device buffer of one session, for tests and profiling ("sbuf": S/L buffer
+ * incl. the L^-1 nu row, "dinv": block inverses / per-phase cycle counters, "wdiag", "mu", "sigma").
+ * Copies min(bytes, size of the buffer); the layout is internal (csrc/rekf_device.cuh). */
+REKF_API int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, size_t bytes);
 
 #ifdef __cplusplus
 }

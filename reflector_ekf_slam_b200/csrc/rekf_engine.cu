@@ -183,7 +183,7 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
   }
   {
     ProfScope p(h, K_SOLVE);
-    if (h->solve_w2) k_solve_w2<<<dim3(L.ld / kW2Cols, 1, L.S), 256, smem_solve_w2(L.rld), h->stream>>>(L);
+    if (h->solve_w2) k_solve_w3<<<dim3(L.ld / kW3Cols, 1, L.S), 256, smem_solve_w3(L.rld), h->stream>>>(L);
     else k_solve_w<<<dim3(L.ld / kWCols, 1, L.S), 256, smem_solve(L), h->stream>>>(L);
   }
   {
@@ -383,9 +383,11 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   if (smem_front(L) > 200 * 1024) return fail(h, REKF_ERR_CAPACITY, "max_landmarks %d needs %zu B of shared memory in k_observation_front", L.Ncap, smem_front(L));
   CK(cudaFuncSetAttribute(k_observation_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_front(L)));
   CK(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol(L)));
-  h->solve_w2 = smem_solve_w2(L.rld) <= 227 * 1024;
-  if (h->solve_w2) CK(cudaFuncSetAttribute(k_solve_w2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w2(L.rld)));
+  h->solve_w2 = smem_solve_w3(L.rld) <= 227 * 1024;
+  if (h->solve_w2) CK(cudaFuncSetAttribute(k_solve_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w3(L.rld)));
   h->chol_resident = smem_chol_resident(L.rcap) <= 227 * 1024;
+  // the resident Cholesky does not emit the diagonal-block inverses the old TRSM kernel needs: use them as a pair
+  h->chol_resident = h->solve_w2 = (h->chol_resident && h->solve_w2);
   if (h->chol_resident)
     CK(cudaFuncSetAttribute(k_cholesky_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(L.rcap)));
   CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
@@ -553,6 +555,25 @@ int rekf_sync(rekf_handle *h) {
     if (st[s].flags & FLAG_TCGEN05_TIMEOUT) return fail(h, REKF_ERR_CUDA, "session %d: tcgen05 SYRK barrier timeout", s);
     if (st[s].flags & (FLAG_LANDMARK_CAPACITY | FLAG_OBS_CAPACITY)) return fail(h, REKF_ERR_CAPACITY, "session %d: capacity exceeded (flags %d)", s, st[s].flags);
   }
+  return REKF_OK;
+}
+
+int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, size_t bytes) {
+  if (!h || !name || !out) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  if (session < 0 || session >= L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
+  const std::string n(name);
+  const void *src = nullptr;
+  size_t size = 0;
+  if (n == "sbuf") { src = L.Sbuf + (size_t)session * L.rld * L.sld; size = sizeof(double) * L.rld * L.sld; }
+  else if (n == "dinv") { src = L.Dinv + (size_t)session * (L.rld / kCholNb) * kCholNb * kCholNb; size = sizeof(double) * (L.rld / kCholNb) * kCholNb * kCholNb; }
+  else if (n == "wdiag" && L.Wdiag) { src = L.Wdiag + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
+  else if (n == "qd") { src = L.Qd + (size_t)session * L.rcap; size = sizeof(double) * L.rcap; }
+  else if (n == "mu") { src = L.mu + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
+  else if (n == "sigma") { src = L.sigma + (size_t)session * L.ld * L.ld; size = sizeof(double) * L.ld * L.ld; }
+  else return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown debug buffer %s", name);
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaMemcpy(out, src, std::min(bytes, size), cudaMemcpyDeviceToHost));
   return REKF_OK;
 }
 

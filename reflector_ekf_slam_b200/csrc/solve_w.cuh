@@ -3,37 +3,41 @@
 // Reference: K_t = Σ·Hᵀ·S⁻¹ and mu += K_t·(z − ẑ) (reflector_ekf_slam.cc:305-307).  With S = L·Lᵀ the gain
 // never has to be formed: W = L⁻¹·H·Σ gives K·ν = Wᵀ·(L⁻¹ν) and K·H·Σ = Wᵀ·W.
 //
-// One CTA = 32 columns of W (32 state slots), 256 threads = 8 warps, lane = column:
+// One CTA = 32 columns of W (32 state slots), 256 threads = 8 warps:
 //   gather   Y[q][c] = Σ_b H[q][b]·Σ[b][c]: H has <= 5 non-zeros per row (:272-275), so each entry is a
 //            16-byte read from row c of the (symmetric) Σ — H·Σ never touches HBM as a matrix;
-//   solve    blocked forward substitution, right-looking, 32-row blocks: W_J = D_J⁻¹·Y_J with the block
-//            inverses from the Cholesky kernel (independent dot products instead of a substitution chain),
-//            then Y_I −= L_IJ·W_J for the rows below.  Each thread keeps its column of W_J in registers;
-//            L is staged through shared memory in 64-row chunks and read as broadcast LDS.128, which is
-//            what lets the fp64 pipe rather than shared-memory bandwidth set the pace;
+//   solve    blocked forward substitution, right-looking, 32-row blocks, entirely on the fp64 tensor pipe
+//            (mma.sync m8n8k4 → DMMA, full rate on B200): W_J = X_J·Y_J with the block inverses X_J = L_JJ⁻¹
+//            the Cholesky kernel emits (no substitution chain), then Y_I −= L_IJ·W_J for the rows below with
+//            W_J's B fragments pinned in registers and L streamed through a swizzled shared-memory chunk;
 //   epilogue μ update (θ wrapped, :307), exact diag(WᵀW), int8 digit slices / tf32 hi-lo / fp64 panels.
 #pragma once
+#include "chol_smem.cuh"
 #include "rekf_device.cuh"
 #include "rekf_kernels.cuh"
 
 namespace rekf {
 
-constexpr int kW2Cols = 32;
-constexpr int kW2YS = kW2Cols + 1;       // padded pitch of the Y/W block
-constexpr int kW2Chunk = 64;             // rows of L staged per pass
+constexpr int kW3Cols = 32;
+constexpr int kW3YS = 36;                // pitch of the Y/W block: B-fragment loads (4 k x 8 n) conflict free
+constexpr int kW3Chunk = 64;             // rows of L staged per pass
 
-inline size_t smem_solve_w2(int rld) {
-  return sizeof(double) * ((size_t)rld * kW2YS + (size_t)kW2Chunk * 32 + 32 * 32) + 64 * sizeof(int);
+inline size_t smem_solve_w3(int rld) {
+  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)kW3Chunk * 32 + 32 * 32) + 64 * sizeof(int);
 }
 
-__global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
+// column swizzle of the 32-wide operand tiles: conflict-free both for row-contiguous staging stores and for the
+// DMMA A-fragment loads (8 rows x 4 k)
+__device__ __forceinline__ int swz(int row) { return ((row & 3) << 2) | ((row >> 2) & 3); }
+
+__global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   extern __shared__ double sm_d[];
   const int s = blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
   const int n = internal_dim(st.N);
-  const int c0 = blockIdx.x * kW2Cols;
+  const int c0 = blockIdx.x * kW3Cols;
   if (c0 >= round_up(n, kSigmaTile)) return;
   const int ld = L.ld, sld = L.sld, rld = L.rld;
   const double *Sg = L.sigma + (size_t)s * ld * ld;
@@ -41,15 +45,17 @@ __global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
   const double *Hp = L.Hp + (size_t)s * L.rcap * 4;
   const double *Hl = L.Hl + (size_t)s * L.rcap * 2;
   const int *Hslot = L.Hslot + (size_t)s * L.rcap;
-  double *Y = sm_d;                                   // [rld][kW2YS]
-  double *Lp = Y + (size_t)rld * kW2YS;               // [64][32] swizzled chunk of an L panel
-  double *Xs = Lp + kW2Chunk * 32;                    // [32][32] inverse of the current diagonal block
+  double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
+  double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [64][32] swizzled chunk of an L panel
+  double *Xs = Lp + kW3Chunk * 32;                    // [32][32] swizzled inverse of the current diagonal block
   int *sexp = reinterpret_cast<int *>(Xs + 32 * 32);  // [32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;             // DMMA fragment coordinates
+  const int nt = warp & 3, rp = warp >> 2;            // this warp's 8-column tile and row-tile parity
   const int r32 = round_up(r, 32);
 
   // ---- gather ----------------------------------------------------------------------------------------
-  for (int cc = warp; cc < kW2Cols; cc += 8) {
+  for (int cc = warp; cc < kW3Cols; cc += 8) {
     const int c = c0 + cc;
     if (c < n) {
       const double *rowc = Sg + (size_t)c * ld;
@@ -65,64 +71,67 @@ __global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
             y += Hl[2 * q] * v.x + Hl[2 * q + 1] * v.y;
           }
         }
-        Y[q * kW2YS + cc] = y;
+        Y[q * kW3YS + cc] = y;
       }
     } else {
-      for (int q = lane; q < r32; q += 32) Y[q * kW2YS + cc] = 0.0;
+      for (int q = lane; q < r32; q += 32) Y[q * kW3YS + cc] = 0.0;
     }
   }
 
-  // ---- blocked forward substitution L·W = Y ---------------------------------------------------------------
+  // ---- blocked forward substitution L·W = Y on the fp64 tensor pipe ---------------------------------------
   const double *Dinv = L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb;
   for (int J = 0; J < r; J += kCholNb) {
     const int jb = min(kCholNb, r - J);
     const double *Dg = Dinv + (size_t)(J / kCholNb) * kCholNb * kCholNb;
-    for (int e = tid; e < 32 * 32; e += 256) Xs[e] = Dg[e];          // zero above the diagonal and past jb
-    __syncthreads();                                                 // also orders the gather / previous update
-    double w[32];
+    for (int e = tid; e < 32 * 32; e += 256) {
+      const int i = e >> 5, k = e & 31;
+      Xs[i * 32 + (k ^ swz(i))] = Dg[e];
+    }
+    __syncthreads();                                  // also orders the gather / previous trailing update
+    // W_J = X_J·Y_J : 4 row tiles x 4 column tiles of 8x8; this warp: column tile nt, row tiles rp and rp+2
+    double w0[2], w1[2];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) w[k] = Y[(J + k) * kW2YS + lane];
-    // W_J = D⁻¹·Y_J : warp handles rows 4·warp .. 4·warp+3 of the block
-    double out[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const double2 *x = reinterpret_cast<const double2 *>(Xs + (4 * warp + u) * 32);
-      double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const double2 xv = x[k];
-        a0 = fma(xv.x, w[2 * k], a0);
-        a1 = fma(xv.y, w[2 * k + 1], a1);
+    for (int h = 0; h < 2; ++h) {
+      const int rt = rp + 2 * h;
+      const int xi = 8 * rt + g;
+      double d0 = 0.0, d1 = 0.0;
+      for (int ks = 0; ks <= 2 * rt + 1; ++ks) {      // X is lower triangular: k <= 8·rt+7
+        const double a = Xs[xi * 32 + ((4 * ks + t4) ^ swz(xi))];
+        const double b = Y[(J + 4 * ks + t4) * kW3YS + 8 * nt + g];
+        dmma884(d0, d1, a, b, d0, d1);
       }
-      out[u] = a0 + a1;
+      w0[h] = d0; w1[h] = d1;
+    }
+    __syncthreads();                                  // every warp has read Y_J
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int rt = rp + 2 * h;
+      *reinterpret_cast<double2 *>(Y + (J + 8 * rt + g) * kW3YS + 8 * nt + 2 * t4) = make_double2(w0[h], w1[h]);
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) Y[(J + 4 * warp + u) * kW2YS + lane] = out[u];
-    __syncthreads();
     if (J + jb >= r) break;
+    double wb[8];                                     // B fragments of W_J for this warp's column tile
 #pragma unroll
-    for (int k = 0; k < 32; ++k) w[k] = Y[(J + k) * kW2YS + lane];   // this thread's column of W_J
-    // rows below: Y[i][:] −= L[i][J..J+32)·W_J, L staged 64 rows at a time (k pairs XOR-swizzled by row)
-    for (int i0 = J + jb; i0 < r; i0 += kW2Chunk) {
-      const int nrows = min(kW2Chunk, r - i0);
-      for (int e = tid; e < kW2Chunk * 32; e += 256) {
-        const int ii = e & (kW2Chunk - 1), k = e >> 6;
+    for (int ks = 0; ks < 8; ++ks) wb[ks] = Y[(J + 4 * ks + t4) * kW3YS + 8 * nt + g];
+    // rows below: Y[i][:] −= L[i][J..J+32)·W_J, L staged 64 rows at a time
+    for (int i0 = J + jb; i0 < r; i0 += kW3Chunk) {
+      const int nrows = min(kW3Chunk, r - i0);
+      for (int e = tid; e < kW3Chunk * 32; e += 256) {
+        const int ii = e & (kW3Chunk - 1), k = e >> 6;
         const double v = (ii < nrows && k < jb) ? Sb[(size_t)(J + k) * sld + i0 + ii] : 0.0;
-        Lp[ii * 32 + (k ^ ((ii & 15) << 1))] = v;
+        Lp[ii * 32 + (k ^ swz(ii))] = v;
       }
       __syncthreads();
-      for (int ii = warp; ii < nrows; ii += 8) {
-        const int sw = (ii & 15) << 1;
-        const double *lrow = Lp + ii * 32;
-        double a0 = 0.0, a1 = 0.0;
+      const int ntile = (nrows + 7) >> 3;
+      for (int rt = rp; rt < ntile; rt += 2) {
+        const int li = 8 * rt + g;
+        double *cp = Y + (i0 + li) * kW3YS + 8 * nt + 2 * t4;
+        const double2 cv = *reinterpret_cast<const double2 *>(cp);
+        double d0 = cv.x, d1 = cv.y;
+        const int sw = swz(li);
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const double2 lv = *reinterpret_cast<const double2 *>(lrow + (k ^ sw));
-          a0 = fma(lv.x, w[k], a0);
-          a1 = fma(lv.y, w[k + 1], a1);
-        }
-        Y[(i0 + ii) * kW2YS + lane] -= a0 + a1;
+        for (int ks = 0; ks < 8; ++ks) dmma884(d0, d1, -Lp[li * 32 + ((4 * ks + t4) ^ sw)], wb[ks], d0, d1);
+        *reinterpret_cast<double2 *>(cp) = make_double2(d0, d1);
       }
       __syncthreads();
     }
@@ -131,11 +140,11 @@ __global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
 
   // ---- μ += Wᵀ·(L⁻¹ν) (:306), θ wrapped (:307); exact diagonal of the downdate -------------------------------
   double *mu = L.mu + (size_t)s * ld;
-  for (int cc = warp; cc < kW2Cols; cc += 8) {
+  for (int cc = warp; cc < kW3Cols; cc += 8) {
     const int c = c0 + cc;
     double a = 0.0, d2 = 0.0, mx = 0.0;
     for (int k = lane; k < r; k += 32) {
-      const double wv = Y[k * kW2YS + cc];
+      const double wv = Y[k * kW3YS + cc];
       a = fma(wv, Sb[(size_t)k * sld + r], a);
       d2 = fma(wv, wv, d2);
       mx = fmax(mx, fabs(wv));
@@ -172,14 +181,14 @@ __global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
   // ---- operand panels of Wᵀ (row c, K contiguous), zero beyond r ---------------------------------------------------
   if (L.W64) {
     double *W = L.W64 + (size_t)s * ld * rld;
-    for (int e = tid; e < kW2Cols * rld; e += 256) {
+    for (int e = tid; e < kW3Cols * rld; e += 256) {
       const int cc = e / rld, k = e - cc * rld;
-      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kW2YS + cc] : 0.0;
+      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kW3YS + cc] : 0.0;
     }
   }
   if (L.Wq) {
     const int kq4 = L.kq / 4;
-    for (int e4 = tid; e4 < kW2Cols * kq4; e4 += 256) {
+    for (int e4 = tid; e4 < kW3Cols * kq4; e4 += 256) {
       const int cc = e4 / kq4, k0 = (e4 - cc * kq4) * 4;
       const int e = sexp[cc];
       const bool live = (c0 + cc < n);
@@ -187,7 +196,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + u;
-        double rem = (live && k < r) ? scalbn(Y[k * kW2YS + cc], 7 - e) : 0.0;
+        double rem = (live && k < r) ? scalbn(Y[k * kW3YS + cc], 7 - e) : 0.0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           const double d = rint(rem);
@@ -201,9 +210,9 @@ __global__ void __launch_bounds__(256, 2) k_solve_w2(Layout L) {
     }
   } else if (L.Wt_hi) {
     float *Wh = L.Wt_hi + (size_t)s * ld * rld, *Wl = L.Wt_lo + (size_t)s * ld * rld;
-    for (int e = tid; e < kW2Cols * rld; e += 256) {
+    for (int e = tid; e < kW3Cols * rld; e += 256) {
       const int cc = e / rld, k = e - cc * rld;
-      const double wv = (k < r) ? Y[k * kW2YS + cc] : 0.0;
+      const double wv = (k < r) ? Y[k * kW3YS + cc] : 0.0;
       const float hi = to_tf32((float)wv);
       const float lo = to_tf32((float)(wv - (double)hi));
       Wh[(size_t)(c0 + cc) * rld + k] = hi;

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rekf_get_mu", "rekf_get_pose", "rekf_batch_get_pose", "rekf_get_landmarks", "rekf_get_sigma", "rekf_get_match_result",
     "rekf_predict_state", "rekf_set_state", "rekf_set_map", "rekf_get_map", "rekf_load_map_txt", "rekf_save_map_txt",
     "rekf_sync", "rekf_stream", "rekf_timer_start", "rekf_timer_stop", "rekf_profile_enable", "rekf_profile_read",
-    "rekf_launch_count", "rekf_device_error_flags",
+    "rekf_launch_count", "rekf_device_error_flags", "rekf_debug_copy",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library(path=None):
         "rekf_profile_read": (i, [vp, P(C.c_char_p), P(d), P(i), i, P(i)]),
         "rekf_launch_count": (C.c_int64, [vp]),
         "rekf_device_error_flags": (i, [vp, i, P(i)]),
+        "rekf_debug_copy": (i, [vp, i, C.c_char_p, vp, C.c_size_t]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -238,6 +239,11 @@ class EKFBatch:
 
     def save_map_txt(self, filebase, s=0):
         self._ck(self.lib.rekf_save_map_txt(self.h, s, filebase.encode()))
+
+    def debug_copy(self, name, count, dtype=np.float64, s=0):
+        out = np.zeros(count, dtype)
+        self._ck(self.lib.rekf_debug_copy(self.h, s, name.encode(), _ptr(out), out.nbytes))
+        return out
 
     def error_flags(self, s=0):
         f = C.c_int()
