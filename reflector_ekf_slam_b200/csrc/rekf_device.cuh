@@ -94,7 +94,8 @@ struct Layout {
   float *Wt_hi, *Wt_lo;  // [S][ld][rld] tf32 hi/lo split of Wᵀ (K-major operands of the tcgen05 SYRK)
   double *W64;    // [S][ld][rld] fp64 Wᵀ (REKF_COV_SIMT_F64 only, else nullptr)
   int8_t *Wq;     // [S][4][ld][kq] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4)
-  int *Wexp;      // [S][ld] per-row power-of-two scale e_c of Wq
+  int *Wexp;      // [S][ld] per-row power-of-two exponent e_c of Wq
+  double *Wscale; // [S][ld] 2^e_c as a double (what the SYRK epilogue multiplies by)
   int kq;         // round_up(rcap, 64): K extent of Wq in bytes
   double *Wdiag;  // [S][ld] exact fp64 diagonal of Wᵀ·W (tensor-core modes use it for Σ[i][i])
   int *step;      // device step counter for replay

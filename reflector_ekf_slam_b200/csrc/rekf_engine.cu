@@ -191,7 +191,7 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
       k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
-      k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);   // exits unless st.exact_update
+      k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);   // exits unless st.exact_update (TODO persistent grid)
       int rc = syrk_i8_launch(h->tc8, L, h->stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -333,6 +333,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     if ((rc = dev_alloc(h, &L.Wq, S * 4 * L.ld * L.kq))) return rc;
     if ((rc = dev_alloc(h, &L.W64, S * L.ld * L.rld))) return rc;
     if ((rc = dev_alloc(h, &L.Wexp, S * L.ld))) return rc;
+    if ((rc = dev_alloc(h, &L.Wscale, S * L.ld))) return rc;
   } else {
     return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown cov_update %d", opts->cov_update);
   }

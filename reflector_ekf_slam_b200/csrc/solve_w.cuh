@@ -23,7 +23,7 @@ constexpr int kW3YS = 36;                // pitch of the Y/W block: B-fragment l
 constexpr int kW3Chunk = 64;             // rows of L staged per pass
 
 inline size_t smem_solve_w3(int rld) {
-  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)kW3Chunk * 32 + 32 * 32) + 64 * sizeof(int);
+  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * kW3Chunk * 32 + 32 * 32) + 64 * sizeof(int);
 }
 
 // column swizzle of the 32-wide operand tiles: conflict-free both for row-contiguous staging stores and for the
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   const double *Hl = L.Hl + (size_t)s * L.rcap * 2;
   const int *Hslot = L.Hslot + (size_t)s * L.rcap;
   double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
-  double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [64][32] swizzled chunk of an L panel
-  double *Xs = Lp + kW3Chunk * 32;                    // [32][32] swizzled inverse of the current diagonal block
+  double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [2][64][32] swizzled chunks of an L panel (double buffer)
+  double *Xs = Lp + 2 * kW3Chunk * 32;                // [32][32] swizzled inverse of the current diagonal block
   int *sexp = reinterpret_cast<int *>(Xs + 32 * 32);  // [32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;             // DMMA fragment coordinates
@@ -55,39 +55,95 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   const int r32 = round_up(r, 32);
 
   // ---- gather ----------------------------------------------------------------------------------------
-  for (int cc = warp; cc < kW3Cols; cc += 8) {
-    const int c = c0 + cc;
-    if (c < n) {
-      const double *rowc = Sg + (size_t)c * ld;
-      const double p0 = rowc[0], p1 = rowc[1], p2 = rowc[2];
-      for (int q = lane; q < r32; q += 32) {
-        double y = 0.0;
-        if (q < r) {
-          const double *h = Hp + 4 * q;
-          y = h[0] * p0 + h[1] * p1 + h[2] * p2;
-          const int slot = Hslot[q];
-          if (slot >= 0) {
-            const double2 v = *reinterpret_cast<const double2 *>(rowc + slot);
-            y += Hl[2 * q] * v.x + Hl[2 * q + 1] * v.y;
+  // The measurement-row descriptors go to shared memory first (one coalesced round trip), so that the only
+  // dependent global access left is the 16-byte read of Σ — and those are issued 2 columns x 8 rows deep.
+  {
+    double *sh = Lp;                                  // [rcap][6]: h0 h1 h2 l0 l1 slot (aliases the L chunk buffers)
+    for (int q = tid; q < r; q += 256) {
+      sh[6 * q + 0] = Hp[4 * q]; sh[6 * q + 1] = Hp[4 * q + 1]; sh[6 * q + 2] = Hp[4 * q + 2];
+      sh[6 * q + 3] = Hl[2 * q]; sh[6 * q + 4] = Hl[2 * q + 1];
+      sh[6 * q + 5] = (double)Hslot[q];
+    }
+    __syncthreads();
+    constexpr int kIt = 8;                            // rows per lane: covers r <= 256
+    for (int cc = warp; cc < kW3Cols; cc += 16) {
+      double2 v[2][kIt];
+      double p[2][3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + cc + 8 * u;
+        const double *rowc = Sg + (size_t)min(c, n - 1) * ld;
+        p[u][0] = rowc[0]; p[u][1] = rowc[1]; p[u][2] = rowc[2];
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int q = lane + 32 * it;
+          const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
+          v[u][it] = (slot >= 0) ? *reinterpret_cast<const double2 *>(rowc + slot) : make_double2(0.0, 0.0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + cc + 8 * u;
+#pragma unroll
+        for (int it = 0; it < kIt; ++it) {
+          const int q = lane + 32 * it;
+          if (q < r32) {
+            double y = 0.0;
+            if (q < r && c < n) {
+              const double *h = sh + 6 * q;
+              y = h[0] * p[u][0] + h[1] * p[u][1] + h[2] * p[u][2];
+              if (h[5] >= 0.0) y += h[3] * v[u][it].x + h[4] * v[u][it].y;
+            }
+            Y[q * kW3YS + cc + 8 * u] = y;
           }
+        }
+      }
+    }
+    for (int q = 256 + tid; q < r32; q += 256)        // rows beyond kIt·32 (only if r > 256): plain path
+      for (int cc = 0; cc < kW3Cols; ++cc) {
+        const int c = c0 + cc;
+        double y = 0.0;
+        if (q < r && c < n) {
+          const double *rowc = Sg + (size_t)c * ld, *h = sh + 6 * q;
+          y = h[0] * rowc[0] + h[1] * rowc[1] + h[2] * rowc[2];
+          if (h[5] >= 0.0) y += h[3] * rowc[(int)h[5]] + h[4] * rowc[(int)h[5] + 1];
         }
         Y[q * kW3YS + cc] = y;
       }
-    } else {
-      for (int q = lane; q < r32; q += 32) Y[q * kW3YS + cc] = 0.0;
-    }
+    __syncthreads();                                  // sh (aliasing Lp) is dead from here on
   }
 
   // ---- blocked forward substitution L·W = Y on the fp64 tensor pipe ---------------------------------------
+  // L chunks and block inverses arrive by cp.async one stage ahead of their use (double-buffered chunks), so
+  // the L2 latency of the operand stream is hidden behind the DMMAs of the previous stage.
   const double *Dinv = L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb;
-  for (int J = 0; J < r; J += kCholNb) {
-    const int jb = min(kCholNb, r - J);
-    const double *Dg = Dinv + (size_t)(J / kCholNb) * kCholNb * kCholNb;
+  auto cp8 = [](double *dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+  };
+  auto stage_X = [&](int Jx) {
+    const double *Dg = Dinv + (size_t)(Jx / kCholNb) * kCholNb * kCholNb;
     for (int e = tid; e < 32 * 32; e += 256) {
       const int i = e >> 5, k = e & 31;
-      Xs[i * 32 + (k ^ swz(i))] = Dg[e];
+      cp8(Xs + i * 32 + (k ^ swz(i)), Dg + e);
     }
-    __syncthreads();                                  // also orders the gather / previous trailing update
+  };
+  auto stage_L = [&](int Js, int i0s, double *buf) {   // rows i0s.. of panel Js (always a full 32-column panel)
+    const int nr = min(kW3Chunk, r - i0s);
+    for (int e = tid; e < kW3Chunk * 32; e += 256) {
+      const int ii = e & (kW3Chunk - 1), k = e >> 6;
+      double *dst = buf + ii * 32 + (k ^ swz(ii));
+      if (ii < nr) cp8(dst, Sb + (size_t)(Js + k) * sld + i0s + ii);
+      else *dst = 0.0;
+    }
+  };
+  int cur = 0;                                        // chunk buffer holding the stage about to be consumed
+  stage_X(0);
+  if (r > kCholNb) stage_L(0, kCholNb, Lp);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int J = 0; J < r; J += kCholNb) {
+    const int jb = min(kCholNb, r - J);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                  // X_J landed; also orders the gather / previous trailing update
     // W_J = X_J·Y_J : 4 row tiles x 4 column tiles of 8x8; this warp: column tile nt, row tiles rp and rp+2
     double w0[2], w1[2];
 #pragma unroll
@@ -102,7 +158,11 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       }
       w0[h] = d0; w1[h] = d1;
     }
-    __syncthreads();                                  // every warp has read Y_J
+    __syncthreads();                                  // every warp has read Y_J and X_J
+    if (J + kCholNb < r) {                            // X of the next block: lands during this block's trailing update
+      stage_X(J + kCholNb);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int rt = rp + 2 * h;
@@ -113,15 +173,20 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     double wb[8];                                     // B fragments of W_J for this warp's column tile
 #pragma unroll
     for (int ks = 0; ks < 8; ++ks) wb[ks] = Y[(J + 4 * ks + t4) * kW3YS + 8 * nt + g];
-    // rows below: Y[i][:] −= L[i][J..J+32)·W_J, L staged 64 rows at a time
+    // rows below: Y[i][:] −= L[i][J..J+32)·W_J, 64 rows of L per stage
     for (int i0 = J + jb; i0 < r; i0 += kW3Chunk) {
       const int nrows = min(kW3Chunk, r - i0);
-      for (int e = tid; e < kW3Chunk * 32; e += 256) {
-        const int ii = e & (kW3Chunk - 1), k = e >> 6;
-        const double v = (ii < nrows && k < jb) ? Sb[(size_t)(J + k) * sld + i0 + ii] : 0.0;
-        Lp[ii * 32 + (k ^ swz(ii))] = v;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();                                // this stage's chunk landed; the other buffer is free again
+      {                                               // prefetch the next stage into the other buffer
+        int Jn = J, in = i0 + kW3Chunk;
+        if (in >= r) { Jn = J + kCholNb; in = Jn + kCholNb; }
+        if (in < r) {
+          stage_L(Jn, in, Lp + (cur ^ 1) * kW3Chunk * 32);
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        }
       }
-      __syncthreads();
+      const double *Lc = Lp + cur * kW3Chunk * 32;
       const int ntile = (nrows + 7) >> 3;
       for (int rt = rp; rt < ntile; rt += 2) {
         const int li = 8 * rt + g;
@@ -130,12 +195,13 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
         double d0 = cv.x, d1 = cv.y;
         const int sw = swz(li);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) dmma884(d0, d1, -Lp[li * 32 + ((4 * ks + t4) ^ sw)], wb[ks], d0, d1);
+        for (int ks = 0; ks < 8; ++ks) dmma884(d0, d1, -Lc[li * 32 + ((4 * ks + t4) ^ sw)], wb[ks], d0, d1);
         *reinterpret_cast<double2 *>(cp) = make_double2(d0, d1);
       }
-      __syncthreads();
+      cur ^= 1;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   // ---- μ += Wᵀ·(L⁻¹ν) (:306), θ wrapped (:307); exact diagonal of the downdate -------------------------------
@@ -167,6 +233,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
         const int e = (mx > 0.0 && c < n) ? ilogb(mx) + 2 : 0;
         sexp[cc] = e;
         L.Wexp[(size_t)s * ld + c] = e;
+        L.Wscale[(size_t)s * ld + c] = scalbn(1.0, e);
         // int8 slices resolve 2^-29 of the row scale 2^e; when the downdate removes almost all of a state's
         // variance that is no longer small against the posterior → this frame takes the fp64 SYRK.
         if (mx > 0.0 && c < n) {
