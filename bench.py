@@ -220,25 +220,8 @@ def run_b200(args):
     if world > 1:
         nb = int(np.ceil(N_LM / M_OBS))
         Ttot = nb + T + EXTRA
-        shard_shape = (S, Ttot, 4 + 1 + 1 + 2 * M_OBS)      # odom | obs_time | count | xy (as float64 payload)
-        recv = torch.empty(shard_shape, dtype=torch.float64, device=dev)
-        if rank == 0:
-            all_streams = build_streams(S * world, T + EXTRA)
-            packed = np.zeros((world,) + shard_shape)
-            for g in range(world):
-                for s in range(S):
-                    st = all_streams[g * S + s]
-                    packed[g, s, :, 0:4] = st["odom"]
-                    packed[g, s, :, 4] = st["obs_time"]
-                    packed[g, s, :, 5] = st["obs_count"]
-                    packed[g, s, :, 6:] = st["obs_xy"].reshape(Ttot, -1)
-            chunks = [torch.tensor(packed[g], device=dev) for g in range(world)]
-            dist.scatter(recv, chunks, src=0)
-        else:
-            dist.scatter(recv, None, src=0)
-        sh = recv.cpu().numpy()
-        streams = [{"odom": sh[s, :, 0:4].copy(), "obs_time": sh[s, :, 4].copy(), "obs_count": sh[s, :, 5].astype(np.int32),
-                    "obs_xy": sh[s, :, 6:].astype(np.float32).reshape(Ttot, M_OBS, 2), "n_build": nb} for s in range(S)]
+        from reflector_ekf_slam_b200.shard import scatter_streams
+        streams = scatter_streams(lambda: build_streams(S * world, T + EXTRA), S, (Ttot, 6 + 2 * M_OBS), nb, dev)
     else:
         streams = build_streams(S, T + EXTRA)
 
