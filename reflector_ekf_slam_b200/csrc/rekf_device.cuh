@@ -25,6 +25,7 @@ constexpr int kCholNb = 32;       // Cholesky / TRSM block size
 constexpr int kWCols = 16;        // columns of W = L⁻¹·H·Σ solved per CTA
 // int8 SYRK admission: (row scale)² / posterior variance above this sends the frame to the fp64 SYRK
 constexpr double kMaxSliceGain2 = 1.0;
+constexpr int kMaxExactSlots = 64;   // more flagged slots than this: the whole frame goes to the fp64 SYRK
 
 enum : int {
   FLAG_LANDMARK_CAPACITY = 1,     // augmentation would exceed max_landmarks: extra reflectors dropped
@@ -46,6 +47,7 @@ struct SessionState {
   int flags;            // sticky FLAG_* bits
   unsigned ticket;      // last-block-done counter (augment kernel)
   int exact_update;     // this frame's downdate cancels too deeply for the int8 slices: use the fp64 SYRK
+  int exact_slots;      // slots whose rows/columns of the downdate are done in fp64 this frame (k_syrk_exact_rows)
 };
 
 // Where the current message comes from: the handle's device mailbox (host path) or device-resident
@@ -98,6 +100,8 @@ struct Layout {
   double *Wscale; // [S][ld] 2^e_c as a double (what the SYRK epilogue multiplies by)
   int kq;         // round_up(rcap, 64): K extent of Wq in bytes
   double *Wdiag;  // [S][ld] exact fp64 diagonal of Wᵀ·W (tensor-core modes use it for Σ[i][i])
+  unsigned char *Wflag;  // [S][ld] 1: this slot's row and column of the downdate are computed in fp64
+  int *exact_list;       // [S][kMaxExactSlots] the flagged slots of this frame
   int *step;      // device step counter for replay
 };
 

@@ -19,6 +19,7 @@
 #include "rekf_kernels.cuh"
 #include "chol_smem.cuh"
 #include "solve_w.cuh"
+#include "syrk_exact_rows.cuh"
 #include "syrk_tcgen05.cuh"
 #include "syrk_tcgen05_i8.cuh"
 
@@ -192,6 +193,7 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
       k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
       k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);   // exits unless st.exact_update (TODO persistent grid)
+      k_syrk_exact_rows<<<dim3((L.ncap + 7) / 8, 8, L.S), 256, 0, h->stream>>>(L);   // fp64 rows/columns of flagged slots
       int rc = syrk_i8_launch(h->tc8, L, h->stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -334,6 +336,8 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     if ((rc = dev_alloc(h, &L.W64, S * L.ld * L.rld))) return rc;
     if ((rc = dev_alloc(h, &L.Wexp, S * L.ld))) return rc;
     if ((rc = dev_alloc(h, &L.Wscale, S * L.ld))) return rc;
+    if ((rc = dev_alloc(h, &L.Wflag, S * L.ld))) return rc;
+    if ((rc = dev_alloc(h, &L.exact_list, S * kMaxExactSlots))) return rc;
   } else {
     return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown cov_update %d", opts->cov_update);
   }
@@ -570,6 +574,7 @@ int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, si
   else if (n == "dinv") { src = L.Dinv + (size_t)session * (L.rld / kCholNb) * kCholNb * kCholNb; size = sizeof(double) * (L.rld / kCholNb) * kCholNb * kCholNb; }
   else if (n == "wdiag" && L.Wdiag) { src = L.Wdiag + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
   else if (n == "qd") { src = L.Qd + (size_t)session * L.rcap; size = sizeof(double) * L.rcap; }
+  else if (n == "state") { src = L.st + session; size = sizeof(SessionState); }
   else if (n == "mu") { src = L.mu + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
   else if (n == "sigma") { src = L.sigma + (size_t)session * L.ld * L.ld; size = sizeof(double) * L.ld * L.ld; }
   else return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown debug buffer %s", name);

@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     st.flags = flags0 | flag_add;
     st.ticket = 0;
     st.exact_update = 0;
+    st.exact_slots = 0;
   }
 }
 

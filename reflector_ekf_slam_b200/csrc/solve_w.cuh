@@ -236,10 +236,20 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
         L.Wscale[(size_t)s * ld + c] = scalbn(1.0, e);
         // int8 slices resolve 2^-29 of the row scale 2^e; when the downdate removes almost all of a state's
         // variance that is no longer small against the posterior → this frame takes the fp64 SYRK.
+        // Such slots are flagged: the tensor kernel skips their rows/columns and k_syrk_exact_rows does them in
+        // fp64.  More than kMaxExactSlots of them (first update after map building: everything collapses) and the
+        // whole frame goes to the fp64 SYRK.
+        bool exact = false;
         if (mx > 0.0 && c < n) {
           const double post = Sg[(size_t)c * ld + c] - d2;
-          if (!(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post) atomicOr(&L.st[s].exact_update, 1);
+          exact = !(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post;
+          if (exact) {
+            const int pos = atomicAdd(&L.st[s].exact_slots, 1);
+            if (pos < kMaxExactSlots) L.exact_list[(size_t)s * kMaxExactSlots + pos] = c;
+            else atomicOr(&L.st[s].exact_update, 1);
+          }
         }
+        L.Wflag[(size_t)s * ld + c] = exact ? 1 : 0;
       }
     }
   }

@@ -1,0 +1,48 @@
+// syrk_exact_rows.cuh — the rows/columns of Σ −= Wᵀ·W that the int8-slice tensor kernel must not touch.
+//
+// The int8 digit slices resolve 2^-29 of a row's scale.  For a state whose variance collapses in this frame
+// (a landmark seen again after a long time, the pose after dead reckoning) that is not small against the
+// posterior, so k_solve_w3 flags such slots (Wflag / exact_list) and the tensor kernel skips every element
+// whose row or column is flagged.  This kernel computes exactly those elements in fp64 from the fp64 panel
+// W64: Σ[a][j] −= Σ_k W[k][a]·W[k][j] for every flagged slot a and every column j, mirrored to Σ[j][a].
+// A pair of flagged slots (a, a') is owned by the smaller index so that it is subtracted once.
+// One warp per element (lanes stride k, shuffle reduction): a handful of flagged slots per frame cost ~n·r
+// FMAs each — microseconds — where routing the whole frame to the fp64 SYRK would cost a millisecond.
+#pragma once
+#include "rekf_device.cuh"
+
+namespace rekf {
+
+__global__ void __launch_bounds__(256) k_syrk_exact_rows(Layout L) {
+  const int s = blockIdx.z;
+  const SessionState &st = L.st[s];
+  const int r = st.r;
+  const int cnt = min(st.exact_slots, kMaxExactSlots);
+  if (r == 0 || cnt == 0 || st.exact_update) return;       // exact_update: the whole frame is done by k_syrk_f64
+  const int n = internal_dim(st.N);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int j = blockIdx.x * 8 + warp;                      // column handled by this warp
+  if (j >= n) return;
+  const int ld = L.ld, rld = L.rld;
+  const double *W = L.W64 + (size_t)s * ld * rld;
+  const unsigned char *flag = L.Wflag + (size_t)s * ld;
+  const int *list = L.exact_list + (size_t)s * kMaxExactSlots;
+  double *Sg = L.sigma + (size_t)s * ld * ld;
+  const double *wj = W + (size_t)j * rld;
+  for (int q = blockIdx.y; q < cnt; q += gridDim.y) {
+    const int a = list[q];
+    if (flag[j] && j < a) continue;                         // (j, a) is owned by row j
+    const double *wa = W + (size_t)a * rld;
+    double acc = 0.0;
+    for (int k = lane; k < r; k += 32) acc = fma(wa[k], wj[k], acc);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      const double v = Sg[(size_t)a * ld + j] - acc;
+      Sg[(size_t)a * ld + j] = v;
+      Sg[(size_t)j * ld + a] = v;
+    }
+  }
+}
+
+}  // namespace rekf

@@ -175,12 +175,14 @@ k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map_a, const __g
     const double *Wsc = L.Wscale + (size_t)s * L.ld;
     const int ld = L.ld;
     const double si = Wsc[min(i, ld - 1)] * 0x1p-35;    // 2^(e_i − 35): the weight of the combined integer sum
+    const unsigned char *flag = L.Wflag + (size_t)s * L.ld;
+    const bool row_ok = !flag[min(i, ld - 1)];           // flagged slots are k_syrk_exact_rows' (fp64)
     const bool above = (i0 + 127 < j0);                 // whole tile strictly above the diagonal
     // the first 16 columns of this thread's Σ row are fetched while the tensor pipe is still busy
     double cur[16];
     {
       const int jbase = j0 + half * 32;
-      const bool want = i < n && jbase < n && !(diag && jbase + 15 < i);
+      const bool want = row_ok && i < n && jbase < n && !(diag && jbase + 15 < i);
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
         cur[u] = cur[u + 1] = cur[u + 2] = cur[u + 3] = 0.0;
@@ -193,7 +195,7 @@ k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map_a, const __g
     for (int chunk = 0; chunk < 2; ++chunk) {
       const int col0 = half * 32 + chunk * 16;
       const int jbase = j0 + col0;
-      const bool want = i < n && jbase < n && !(diag && jbase + 15 < i);
+      const bool want = row_ok && i < n && jbase < n && !(diag && jbase + 15 < i);
       double *row = Sg + (size_t)i * ld + jbase;
       if (chunk == 1 && want) {
 #pragma unroll
@@ -238,7 +240,9 @@ k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
           for (int u = 0; u < 16; ++u) if (u == ud) cur[u] = dd;
         }
-        if (above && jbase + 15 < n) {
+        const uint4 cf = *reinterpret_cast<const uint4 *>(flag + min(jbase, ld - 16));   // 16 column flags, warp-uniform
+        const bool cols_ok = (cf.x | cf.y | cf.z | cf.w) == 0u;
+        if (above && cols_ok && jbase + 15 < n) {
 #pragma unroll
           for (int u = 0; u < 16; u += 4) stg256(row + u, cur + u);     // full 32-byte sectors
 #pragma unroll
@@ -247,7 +251,8 @@ k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map_a, const __g
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int j = jbase + u;
-            if (j < n && i <= j) {
+            const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+            if (j < n && i <= j && !((cfw >> (8 * (u & 3))) & 0xffu)) {
               row[u] = cur[u];
               if (i != j) Sg[(size_t)j * ld + i] = cur[u];
             }
