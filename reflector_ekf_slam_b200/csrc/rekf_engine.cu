@@ -22,6 +22,7 @@
 #include "syrk_exact_rows.cuh"
 #include "syrk_tcgen05.cuh"
 #include "syrk_tcgen05_i8.cuh"
+#include "syrk_tcgen05_i8p.cuh"
 
 using namespace rekf;
 
@@ -71,6 +72,8 @@ struct rekf_handle {
   bool chol_resident = false, solve_w2 = false;
   SyrkTc tc{};
   SyrkI8 tc8{};
+  SyrkI8P tc8p{};
+  bool persistent_syrk = true;
   std::vector<void *> allocations;
 };
 
@@ -190,11 +193,11 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
   {
     ProfScope p(h, K_SYRK);
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
-      k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);
+      k_syrk_f64<<<dim3(592, 1, L.S), 256, 0, h->stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
-      k_syrk_f64<<<dim3(L.ld / 64, L.ld / 64, L.S), 256, 0, h->stream>>>(L);   // exits unless st.exact_update (TODO persistent grid)
+      k_syrk_f64<<<dim3(148, 1, L.S), 256, 0, h->stream>>>(L);   // exits at once unless st.exact_update
       k_syrk_exact_rows<<<dim3((L.ncap + 7) / 8, 8, L.S), 256, 0, h->stream>>>(L);   // fp64 rows/columns of flagged slots
-      int rc = syrk_i8_launch(h->tc8, L, h->stream);
+      int rc = h->persistent_syrk ? syrk_i8p_launch(h->tc8p, L, h->stream) : syrk_i8_launch(h->tc8, L, h->stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
       int rc = syrk_tc_launch(h->tc, L, h->stream);
@@ -402,7 +405,9 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK setup failed: %s", why);
   }
   if (opts->cov_update == REKF_COV_TCGEN05_I8X4) {
+    h->persistent_syrk = std::getenv("REKF_SYRK_NONPERSISTENT") == nullptr;
     const char *why = syrk_i8_init(h->tc8, L);
+    if (!why) why = syrk_i8p_init(h->tc8p, L);
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK setup failed: %s", why);
   }
   if (opts->map_path && opts->map_path[0]) rekf_load_map_txt(h, opts->map_path);   // :36

@@ -680,12 +680,14 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
   const int s = blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
-  const int ti = blockIdx.y, tj = blockIdx.x;
-  if (r == 0 || ti > tj) return;
+  if (r == 0) return;
   if (L.Wq && !st.exact_update) return;     // int8 tensor-core SYRK handles this frame
   const int n = internal_dim(st.N);
+  const int Tn = L.ld / 64;
+  for (int tile = blockIdx.x; tile < Tn * Tn; tile += gridDim.x) {   // grid-stride over tiles: a cheap no-op launch
+  const int ti = tile / Tn, tj = tile - ti * Tn;
   const int i0 = ti * 64, j0 = tj * 64;
-  if (j0 >= n) return;
+  if (ti > tj || j0 >= n) continue;
   const int rld = L.rld, ld = L.ld;
   const double *W = L.W64 + (size_t)s * ld * rld;
   double *Sg = L.sigma + (size_t)s * ld * ld;
@@ -726,6 +728,8 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
         Sg[(size_t)j * ld + i] = val;
       }
     }
+  __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,380 @@
+// syrk_tcgen05_i8p.cuh — persistent, fully overlapped form of the exact int8-slice covariance SYRK
+// (Σ −= Wᵀ·W, reflector_ekf_slam.cc:308; arithmetic identical to syrk_tcgen05_i8.cuh — see there for the
+// digit-slice scheme).  What changes is the data movement, because the kernel is HBM-bound:
+//
+//   * one CTA per SM loops over (session, tile) work items: 128x64 tiles on/above the diagonal;
+//   * Σ tiles travel by TMA in both directions: two 128-row x 32-column half-tiles (4 boxes of 16 columns, 128-byte
+//     swizzle) are double-buffered in shared memory — full-line HBM reads issued a whole tile ahead, full-line
+//     writes, no partial sectors, no L1 thrash; only the mirrored lower-triangle copy is written from registers
+//     (coalesced across lanes);
+//   * the s32 accumulators are double-buffered in TMEM (2 x 4 x 64 columns = all 512), so the tensor pipe works on
+//     tile t+1 while the epilogue warps drain tile t;
+//   * warp roles: 0-7 epilogue, 8 operand TMA producer (2-stage ring of int8 slice boxes), 9 MMA issuer
+//     (tcgen05.mma.kind::i8), 10 Σ-tile TMA loader.
+// Tiles that touch the diagonal (34 of 306 at C3) keep the direct global-memory epilogue: their lower triangle is
+// written as mirror elements by the same CTA, which a whole-box TMA store would race with.
+#pragma once
+#include "syrk_tcgen05_i8.cuh"
+
+namespace rekf {
+
+constexpr int kPThreads = 384;                           // 12 warps: 8 epilogue, operand TMA, MMA, Σ load, Σ store
+constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ: 128 rows x 32 columns fp64 = 32 KB
+constexpr int kPSmemBytes = kI8Stages * kI8StageBytes + 2 * kPSigHalf + 1024 + 256;
+
+struct SyrkI8P {
+  CUtensorMap map_a, map_b, map_sig;
+  int num_sms = 148;
+  bool ready = false;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// waits of the single-thread roles back off between probes so that they do not steal issue slots from the epilogue
+__device__ __forceinline__ bool mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (kSpinLimit >> 4); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return true;
+    __nanosleep(64);
+  }
+  return false;
+}
+// exact int64 → double for |g| < 2^51 without the slow I2F.F64.S64: add to the bits of 2^52+2^51, subtract it back
+__device__ __forceinline__ double i64_to_f64(long long g) {
+  return __longlong_as_double(g + 0x4338000000000000LL) - 6755399441055744.0;
+}
+
+__global__ void __launch_bounds__(kPThreads, 1)
+k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_sig) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t *ops = base;                                   // [2][48 KB] int8 slice boxes
+  uint8_t *sig = base + kI8Stages * kI8StageBytes;       // [2][32 KB] Σ half-tiles
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sig + 2 * kPSigHalf);
+  uint64_t *op_full = bars, *op_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6, *sig_full = bars + 8,
+           *sig_empty = bars + 10, *sig_done = bars + 12;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Tn64 = L.ld / kI8TileN;
+  const int tiles = (L.ld / 128) * (L.ld / 128 + 1);
+  const int total = tiles * L.S;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&op_full[i], 1); mbar_init(&op_empty[i], 1);
+        mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256);
+        mbar_init(&sig_full[i], 1); mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], 256);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  bool timeout = false;
+
+  // every role walks the same item sequence and applies the same skip rule
+  auto decode = [&](int item, int &s, int &i0, int &j0, int &r, int &n, bool &inA) -> bool {
+    s = item / tiles;
+    int rem = item - s * tiles, ti = 0;
+    while (rem >= Tn64 - 2 * ti) { rem -= Tn64 - 2 * ti; ++ti; }
+    const int tj = 2 * ti + rem;
+    i0 = ti * 128; j0 = tj * kI8TileN;
+    inA = rem < 2;
+    const SessionState &st = L.st[s];
+    r = st.r; n = internal_dim(st.N);
+    return r > 0 && !st.exact_update && j0 < n;
+  };
+
+  if (warp == 8) {
+    // ===== operand TMA producer =====
+    if (lane == 0) {
+      uint32_t kbc = 0;
+      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+        int s, i0, j0, r, n; bool inA;
+        if (!decode(item, s, i0, j0, r, n, inA)) continue;
+        const int nkb = (r + kI8KBox - 1) / kI8KBox;
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int stage = kbc & 1;
+          if (!mbar_wait_backoff(&op_empty[stage], ((kbc >> 1) & 1) ^ 1)) { timeout = true; break; }
+          uint8_t *sa = ops + (size_t)stage * kI8StageBytes, *sb = sa + kI8Slices * kI8BoxA;
+          mbar_expect_tx(&op_full[stage], kI8Slices * (kI8BoxA + (inA ? 0 : kI8BoxB)));
+#pragma unroll
+          for (int p = 0; p < kI8Slices; ++p) {
+            tma_load_4d(sa + p * kI8BoxA, &map_a, &op_full[stage], kb * kI8KBox, i0, p, s);
+            if (!inA) tma_load_4d(sb + p * kI8BoxB, &map_b, &op_full[stage], kb * kI8KBox, j0, p, s);
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      uint32_t kbc = 0, iter = 0;
+      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+        int s, i0, j0, r, n; bool inA;
+        if (!decode(item, s, i0, j0, r, n, inA)) continue;
+        const int set = iter & 1;
+        if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
+        tc_fence_after();
+        const uint32_t acc = tmem + set * 256;
+        const int nkb = (r + kI8KBox - 1) / kI8KBox, nk32 = (r + 31) / 32;
+        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
+          const int stage = kbc & 1;
+          if (!mbar_wait_backoff(&op_full[stage], (kbc >> 1) & 1)) { timeout = true; break; }
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ops + (size_t)stage * kI8StageBytes);
+          const uint32_t sb = inA ? sa + (uint32_t)(j0 - i0) * kI8KBox : sa + kI8Slices * kI8BoxA;
+          const uint32_t bstride = inA ? kI8BoxA : kI8BoxB;
+          const int steps = min(2, nk32 - kb * 2);
+          for (int ks = 0; ks < steps; ++ks) {
+            const uint32_t koff = ks * 32;
+            const bool first = (kb | ks) == 0;
+#pragma unroll
+            for (int sgrp = 0; sgrp < kI8Slices; ++sgrp) {
+#pragma unroll
+              for (int p = 0; p <= sgrp; ++p) {
+                const int q = sgrp - p;
+                tc_mma_i8(acc + sgrp * kI8TileN, make_kmajor_sw64_desc(sa + p * kI8BoxA + koff),
+                          make_kmajor_sw64_desc(sb + q * bstride + koff), kIdescI8, (first && p == 0) ? 0u : 1u);
+              }
+            }
+          }
+          tc_commit(&op_empty[stage]);
+        }
+        tc_commit(&acc_full[set]);
+        ++iter;
+      }
+    }
+  } else if (warp == 10) {
+    // ===== Σ-tile TMA loader (tiles strictly above the diagonal) =====
+    if (lane == 0) {
+      uint32_t sit = 0;
+      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+        int s, i0, j0, r, n; bool inA;
+        if (!decode(item, s, i0, j0, r, n, inA) || inA) continue;
+        for (int h = 0; h < 2; ++h) {
+          if (!mbar_wait_backoff(&sig_empty[h], (sit & 1) ^ 1)) { timeout = true; break; }
+          uint8_t *dst = sig + (size_t)h * kPSigHalf;
+          mbar_expect_tx(&sig_full[h], kPSigHalf);
+          tma_load_3d(dst, &map_sig, &sig_full[h], j0 + 32 * h, i0, s);
+          tma_load_3d(dst + kPSigHalf / 2, &map_sig, &sig_full[h], j0 + 32 * h + 16, i0, s);
+        }
+        ++sit;
+      }
+    }
+  } else if (warp == 11) {
+    // ===== Σ-tile TMA store: waits until the 256 epilogue threads have rewritten a half-tile, stores it, frees it =====
+    if (lane == 0) {
+      uint32_t sit = 0;
+      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+        int s, i0, j0, r, n; bool inA;
+        if (!decode(item, s, i0, j0, r, n, inA) || inA) continue;
+        for (int h = 0; h < 2; ++h) {
+          if (!mbar_wait_backoff(&sig_done[h], sit & 1)) { timeout = true; break; }
+          const uint8_t *src = sig + (size_t)h * kPSigHalf;
+          tma_store_3d(&map_sig, src, j0 + 32 * h, i0, s);
+          tma_store_3d(&map_sig, src + kPSigHalf / 2, j0 + 32 * h + 16, i0, s);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(&sig_empty[h]);
+        }
+        ++sit;
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all Σ stores landed
+    }
+  } else if (warp < 8) {
+    // ===== epilogue: warp w owns TMEM lanes 32·(w%4).. ; within a 32-column half-tile, columns 16·(w/4).. =====
+    const int quad = warp & 3, halfw = warp >> 2;
+    const int il = quad * 32 + lane;                     // row inside the tile
+    uint32_t iter = 0, sit = 0;
+    const int ld = L.ld;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      int s, i0, j0, r, n; bool inA;
+      if (!decode(item, s, i0, j0, r, n, inA)) continue;
+      const int set = iter & 1;
+      const int i = i0 + il;
+      double *Sg = L.sigma + (size_t)s * ld * ld;
+      const double *Wsc = L.Wscale + (size_t)s * ld;
+      const unsigned char *flag = L.Wflag + (size_t)s * ld;
+      const double si = Wsc[min(i, ld - 1)] * 0x1p-35;
+      const bool row_ok = !flag[min(i, ld - 1)];
+      if (!mbar_wait(&acc_full[set], (iter >> 1) & 1)) timeout = true;
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int col0 = 32 * h + 16 * halfw;            // first of this thread's 16 tile columns
+        const int jbase = j0 + col0;
+        const uint32_t taddr = tmem + set * 256 + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
+        long long G[16];
+        {
+          uint32_t gq[16];
+          tc_ld16(taddr, gq);
+          tc_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) G[u] = (long long)(int)gq[u] << 21;
+          tc_ld16(taddr + kI8TileN, gq);
+          tc_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) G[u] += (long long)(int)gq[u] << 14;
+          tc_ld16(taddr + 2 * kI8TileN, gq);
+          tc_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) G[u] += (long long)(int)gq[u] << 7;
+          tc_ld16(taddr + 3 * kI8TileN, gq);
+          tc_wait_ld();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) G[u] += (long long)(int)gq[u];
+        }
+        const uint4 cf = *reinterpret_cast<const uint4 *>(flag + min(jbase, ld - 16));
+        const double2 *scj = reinterpret_cast<const double2 *>(Wsc + min(jbase, ld - 16));
+        double cur[16];
+        if (!inA) {
+          // ---- Σ half-tile staged by TMA: read own row (swizzled 16-byte chunks), update, write back, TMA store ----
+          if (!mbar_wait(&sig_full[h], sit & 1)) timeout = true;
+          uint8_t *rowp = sig + (size_t)h * kPSigHalf + (size_t)halfw * (kPSigHalf / 2) + (size_t)il * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double2 t = *reinterpret_cast<const double2 *>(rowp + ((c ^ (il & 7)) << 4));
+            cur[2 * c] = t.x; cur[2 * c + 1] = t.y;
+          }
+          const bool no_flags = row_ok && (cf.x | cf.y | cf.z | cf.w) == 0u;   // the common case, warp-uniform but for row_ok
+          if (no_flags) {
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+              const double2 sj = scj[u >> 1];
+              cur[u] = fma(-i64_to_f64(G[u]), si * sj.x, cur[u]);
+              cur[u + 1] = fma(-i64_to_f64(G[u + 1]), si * sj.y, cur[u + 1]);
+            }
+          } else if (row_ok) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+              if (!((cfw >> (8 * (u & 3))) & 0xffu)) cur[u] = fma(-i64_to_f64(G[u]), si * Wsc[min(jbase + u, ld - 1)], cur[u]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<double2 *>(rowp + ((c ^ (il & 7)) << 4)) = make_double2(cur[2 * c], cur[2 * c + 1]);
+          // mirrored lower-triangle copy straight from registers (lanes = consecutive rows: coalesced)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(&sig_done[h]);                        // hand the half-tile to the store warp
+          if (no_flags && i < n && jbase + 15 < n) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
+          } else if (row_ok && i < n) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+              if (jbase + u < n && !((cfw >> (8 * (u & 3))) & 0xffu)) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
+            }
+          }
+        } else {
+          // ---- diagonal tile: direct global accesses, element predicates (i <= j), exact diagonal ----
+          const bool want = row_ok && i < n && jbase < n && !(jbase + 15 < i);
+          if (want) {
+            double *row = Sg + (size_t)i * ld + jbase;
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) ldg256(row + u, cur + u);
+            const int ud = i - jbase;
+            double old_diag = 0.0;
+#pragma unroll
+            for (int u = 0; u < 16; u += 2) {
+              const double2 sj = scj[u >> 1];
+              if (u == ud) old_diag = cur[u];
+              if (u + 1 == ud) old_diag = cur[u + 1];
+              cur[u] = fma(-i64_to_f64(G[u]), si * sj.x, cur[u]);
+              cur[u + 1] = fma(-i64_to_f64(G[u + 1]), si * sj.y, cur[u + 1]);
+            }
+            if (ud >= 0 && ud < 16) {
+              const double dd = old_diag - L.Wdiag[(size_t)s * ld + i];
+#pragma unroll
+              for (int u = 0; u < 16; ++u) if (u == ud) cur[u] = dd;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const int j = jbase + u;
+              const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+              if (j < n && i <= j && !((cfw >> (8 * (u & 3))) & 0xffu)) {
+                row[u] = cur[u];
+                if (i != j) Sg[(size_t)j * ld + i] = cur[u];
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[set]);                      // this thread is done with the accumulator set
+      ++iter;
+      if (!inA) ++sit;
+    }
+  }
+  if (timeout) atomicOr(&L.st[0].flags, FLAG_TCGEN05_TIMEOUT);
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+inline const char *syrk_i8p_init(SyrkI8P &tc, const Layout &L) {
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess)
+    return "cuTensorMapEncodeTiled entry point not available";
+  PFN_encodeTiled encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  const cuuint64_t dims[4] = {(cuuint64_t)L.kq, (cuuint64_t)L.ld, (cuuint64_t)kI8Slices, (cuuint64_t)L.S};
+  const cuuint64_t strides[3] = {(cuuint64_t)L.kq, (cuuint64_t)L.ld * L.kq, (cuuint64_t)kI8Slices * L.ld * L.kq};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  const cuuint32_t box_a[4] = {(cuuint32_t)kI8KBox, 128u, 1u, 1u};
+  const cuuint32_t box_b[4] = {(cuuint32_t)kI8KBox, (cuuint32_t)kI8TileN, 1u, 1u};
+  if (encode(&tc.map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, L.Wq, dims, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return "cuTensorMapEncodeTiled(Wq, A box) failed";
+  if (encode(&tc.map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, L.Wq, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return "cuTensorMapEncodeTiled(Wq, B box) failed";
+  const cuuint64_t sdims[3] = {(cuuint64_t)L.ld, (cuuint64_t)L.ld, (cuuint64_t)L.S};
+  const cuuint64_t sstrides[2] = {(cuuint64_t)L.ld * sizeof(double), (cuuint64_t)L.ld * L.ld * sizeof(double)};
+  const cuuint32_t sbox[3] = {16u, 128u, 1u};
+  const cuuint32_t sestr[3] = {1u, 1u, 1u};
+  if (encode(&tc.map_sig, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.sigma, sdims, sstrides, sbox, sestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return "cuTensorMapEncodeTiled(Sigma) failed";
+  if (cudaFuncSetAttribute(k_syrk_tcgen05_i8p, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes) != cudaSuccess)
+    return "cudaFuncSetAttribute(k_syrk_tcgen05_i8p, smem) failed";
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&tc.num_sms, cudaDevAttrMultiProcessorCount, dev);
+  tc.ready = true;
+  return nullptr;
+}
+
+inline int syrk_i8p_launch(const SyrkI8P &tc, const Layout &L, cudaStream_t stream) {
+  if (!tc.ready) return -1;
+  const int total = (L.ld / 128) * (L.ld / 128 + 1) * L.S;
+  const int grid = total < tc.num_sms ? total : tc.num_sms;
+  k_syrk_tcgen05_i8p<<<grid, kPThreads, kPSmemBytes, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
+  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace rekf
