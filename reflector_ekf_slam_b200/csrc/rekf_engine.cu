@@ -578,6 +578,7 @@ int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, si
   if (n == "sbuf") { src = L.Sbuf + (size_t)session * L.rld * L.sld; size = sizeof(double) * L.rld * L.sld; }
   else if (n == "dinv") { src = L.Dinv + (size_t)session * (L.rld / kCholNb) * kCholNb * kCholNb; size = sizeof(double) * (L.rld / kCholNb) * kCholNb * kCholNb; }
   else if (n == "wdiag" && L.Wdiag) { src = L.Wdiag + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
+  else if (n == "innov") { src = L.innov + (size_t)session * L.rcap; size = sizeof(double) * L.rcap; }
   else if (n == "qd") { src = L.Qd + (size_t)session * L.rcap; size = sizeof(double) * L.rcap; }
   else if (n == "state") { src = L.st + session; size = sizeof(SessionState); }
   else if (n == "mu") { src = L.mu + (size_t)session * L.ld; size = sizeof(double) * L.ld; }

@@ -23,7 +23,7 @@ constexpr int kW3YS = 36;                // pitch of the Y/W block: B-fragment l
 constexpr int kW3Chunk = 64;             // rows of L staged per pass
 
 inline size_t smem_solve_w3(int rld) {
-  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * kW3Chunk * 32 + 32 * 32) + 64 * sizeof(int);
+  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * kW3Chunk * 32 + 32 * 32 + rld) + 64 * sizeof(int);
 }
 
 // column swizzle of the 32-wide operand tiles: conflict-free both for row-contiguous staging stores and for the
@@ -48,11 +48,21 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
   double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [2][64][32] swizzled chunks of an L panel (double buffer)
   double *Xs = Lp + 2 * kW3Chunk * 32;                // [32][32] swizzled inverse of the current diagonal block
-  int *sexp = reinterpret_cast<int *>(Xs + 32 * 32);  // [32]
+  double *nu = Xs + 32 * 32;                          // [rld] L⁻¹ν (row r of the factor), staged once
+  int *sexp = reinterpret_cast<int *>(nu + rld);      // [32]
+  for (int k = threadIdx.x; k < r; k += 256) nu[k] = Sb[(size_t)k * sld + r];   // visible after the gather's barriers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;             // DMMA fragment coordinates
   const int nt = warp & 3, rp = warp >> 2;            // this warp's 8-column tile and row-tile parity
   const int r32 = round_up(r, 32);
+#ifdef REKF_SOLVE_TIMING
+  double *tlog = L.innov + (size_t)s * L.rcap;        // cycle stamps of CTA 0 (thread 0)
+  int tl = 0;
+#define REKF_WSTAMP() do { if (tid == 0 && blockIdx.x == 0) tlog[tl++] = (double)clock64(); } while (0)
+#else
+#define REKF_WSTAMP() do { } while (0)
+#endif
+  REKF_WSTAMP();
 
   // ---- gather ----------------------------------------------------------------------------------------
   // The measurement-row descriptors go to shared memory first (one coalesced round trip), so that the only
@@ -112,6 +122,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       }
     __syncthreads();                                  // sh (aliasing Lp) is dead from here on
   }
+  REKF_WSTAMP();
 
   // ---- blocked forward substitution L·W = Y on the fp64 tensor pipe ---------------------------------------
   // L chunks and block inverses arrive by cp.async one stage ahead of their use (double-buffered chunks), so
@@ -144,19 +155,18 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     const int jb = min(kCholNb, r - J);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                  // X_J landed; also orders the gather / previous trailing update
+    REKF_WSTAMP();
     // W_J = X_J·Y_J : 4 row tiles x 4 column tiles of 8x8; this warp: column tile nt, row tiles rp and rp+2
     double w0[2], w1[2];
+    w0[0] = w0[1] = w1[0] = w1[1] = 0.0;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int rt = rp + 2 * h;
-      const int xi = 8 * rt + g;
-      double d0 = 0.0, d1 = 0.0;
-      for (int ks = 0; ks <= 2 * rt + 1; ++ks) {      // X is lower triangular: k <= 8·rt+7
-        const double a = Xs[xi * 32 + ((4 * ks + t4) ^ swz(xi))];
-        const double b = Y[(J + 4 * ks + t4) * kW3YS + 8 * nt + g];
-        dmma884(d0, d1, a, b, d0, d1);
+    for (int ks = 0; ks < 8; ++ks) {                  // two independent chains; X is zero above its diagonal
+      const double b = Y[(J + 4 * ks + t4) * kW3YS + 8 * nt + g];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int xi = 8 * (rp + 2 * h) + g;
+        dmma884(w0[h], w1[h], Xs[xi * 32 + ((4 * ks + t4) ^ swz(xi))], b, w0[h], w1[h]);
       }
-      w0[h] = d0; w1[h] = d1;
     }
     __syncthreads();                                  // every warp has read Y_J and X_J
     if (J + kCholNb < r) {                            // X of the next block: lands during this block's trailing update
@@ -169,6 +179,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       *reinterpret_cast<double2 *>(Y + (J + 8 * rt + g) * kW3YS + 8 * nt + 2 * t4) = make_double2(w0[h], w1[h]);
     }
     __syncthreads();
+    REKF_WSTAMP();
     if (J + jb >= r) break;
     double wb[8];                                     // B fragments of W_J for this warp's column tile
 #pragma unroll
@@ -188,21 +199,33 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       }
       const double *Lc = Lp + cur * kW3Chunk * 32;
       const int ntile = (nrows + 7) >> 3;
-      for (int rt = rp; rt < ntile; rt += 2) {
-        const int li = 8 * rt + g;
-        double *cp = Y + (i0 + li) * kW3YS + 8 * nt + 2 * t4;
-        const double2 cv = *reinterpret_cast<const double2 *>(cp);
-        double d0 = cv.x, d1 = cv.y;
-        const int sw = swz(li);
+      // this warp's (up to) four row tiles of the chunk as four independent DMMA chains
+      double d0[4], d1[4];
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) dmma884(d0, d1, -Lc[li * 32 + ((4 * ks + t4) ^ sw)], wb[ks], d0, d1);
-        *reinterpret_cast<double2 *>(cp) = make_double2(d0, d1);
+      for (int q = 0; q < 4; ++q) {
+        const int rt = rp + 2 * q;                      // rows past nrows are zero-filled in Lc: harmless
+        const double2 cv = *reinterpret_cast<const double2 *>(Y + min(i0 + 8 * rt + g, rld + 7) * kW3YS + 8 * nt + 2 * t4);
+        d0[q] = cv.x; d1[q] = cv.y;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int li = 8 * (rp + 2 * q) + g;
+          dmma884(d0[q], d1[q], -Lc[li * 32 + ((4 * ks + t4) ^ swz(li))], wb[ks], d0[q], d1[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int rt = rp + 2 * q;
+        if (rt < ntile) *reinterpret_cast<double2 *>(Y + (i0 + 8 * rt + g) * kW3YS + 8 * nt + 2 * t4) = make_double2(d0[q], d1[q]);
       }
       cur ^= 1;
     }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  REKF_WSTAMP();
 
   // ---- μ += Wᵀ·(L⁻¹ν) (:306), θ wrapped (:307); exact diagonal of the downdate -------------------------------
   double *mu = L.mu + (size_t)s * ld;
@@ -211,7 +234,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     double a = 0.0, d2 = 0.0, mx = 0.0;
     for (int k = lane; k < r; k += 32) {
       const double wv = Y[k * kW3YS + cc];
-      a = fma(wv, Sb[(size_t)k * sld + r], a);
+      a = fma(wv, nu[k], a);
       d2 = fma(wv, wv, d2);
       mx = fmax(mx, fabs(wv));
     }
@@ -254,6 +277,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     }
   }
   __syncthreads();
+  REKF_WSTAMP();
 
   // ---- operand panels of Wᵀ (row c, K contiguous), zero beyond r ---------------------------------------------------
   if (L.W64) {
@@ -264,20 +288,23 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     }
   }
   if (L.Wq) {
+    // x = w·2^-e, |x| <= 1/2, x ≈ Σ_p d_p·2^(-7(p+1)); d_p = rint(·) by magic-number addition (exact, no cvt / libm)
+    const double kMagic = 6755399441055744.0;          // 2^52 + 2^51
     const int kq4 = L.kq / 4;
     for (int e4 = tid; e4 < kW3Cols * kq4; e4 += 256) {
       const int cc = e4 / kq4, k0 = (e4 - cc * kq4) * 4;
-      const int e = sexp[cc];
       const bool live = (c0 + cc < n);
+      const double sc = __longlong_as_double((long long)(1023 + 7 - sexp[cc]) << 52);   // 2^(7-e)
       uint32_t packed[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + u;
-        double rem = (live && k < r) ? scalbn(Y[k * kW3YS + cc], 7 - e) : 0.0;
+        double rem = (live && k < r) ? Y[k * kW3YS + cc] * sc : 0.0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const double d = rint(rem);
-          packed[p] |= ((uint32_t)(int)d & 0xffu) << (8 * u);
+          const double t = rem + kMagic;
+          const double d = t - kMagic;                 // rint(rem)
+          packed[p] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * u);
           rem = (rem - d) * 128.0;
         }
       }
@@ -296,6 +323,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       Wl[(size_t)(c0 + cc) * rld + k] = lo;
     }
   }
+  REKF_WSTAMP();
 }
 
 }  // namespace rekf
