@@ -21,9 +21,10 @@ namespace rekf {
 constexpr int kW3Cols = 32;
 constexpr int kW3YS = 36;                // pitch of the Y/W block: B-fragment loads (4 k x 8 n) conflict free
 constexpr int kW3Chunk = 64;             // rows of L staged per pass
+constexpr int kW3LP = kW3Chunk + 4;      // pitch of a staged L chunk, k-major [32 k][68]: A-fragment loads conflict free
 
 inline size_t smem_solve_w3(int rld) {
-  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * kW3Chunk * 32 + 32 * 32 + rld) + 64 * sizeof(int);
+  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * 32 * kW3LP + 32 * 32 + rld) + 64 * sizeof(int);
 }
 
 // column swizzle of the 32-wide operand tiles: conflict-free both for row-contiguous staging stores and for the
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   const int *Hslot = L.Hslot + (size_t)s * L.rcap;
   double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
   double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [2][64][32] swizzled chunks of an L panel (double buffer)
-  double *Xs = Lp + 2 * kW3Chunk * 32;                // [32][32] swizzled inverse of the current diagonal block
+  double *Xs = Lp + 2 * 32 * kW3LP;                   // [32][32] swizzled inverse of the current diagonal block
   double *nu = Xs + 32 * 32;                          // [rld] L⁻¹ν (row r of the factor), staged once
   int *sexp = reinterpret_cast<int *>(nu + rld);      // [32]
   for (int k = threadIdx.x; k < r; k += 256) nu[k] = Sb[(size_t)k * sld + r];   // visible after the gather's barriers
@@ -75,51 +76,35 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       sh[6 * q + 5] = (double)Hslot[q];
     }
     __syncthreads();
-    constexpr int kIt = 8;                            // rows per lane: covers r <= 256
-    for (int cc = warp; cc < kW3Cols; cc += 16) {
-      double2 v[2][kIt];
-      double p[2][3];
+    // lane = column (its Σ row and pose entries stay in registers), warps stride the measurement rows: the row
+    // descriptor is one broadcast read, the Y store is conflict free, eight Σ reads are in flight per lane
+    const int c = c0 + lane;
+    const bool live = c < n;
+    const double *rowc = Sg + (size_t)min(c, n - 1) * ld;
+    const double p0 = rowc[0], p1 = rowc[1], p2 = rowc[2];
+    constexpr int kIt = 8;
+    for (int qb = warp; qb < r32; qb += 8 * kIt) {
+      double2 v[kIt];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = c0 + cc + 8 * u;
-        const double *rowc = Sg + (size_t)min(c, n - 1) * ld;
-        p[u][0] = rowc[0]; p[u][1] = rowc[1]; p[u][2] = rowc[2];
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-          const int q = lane + 32 * it;
-          const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
-          v[u][it] = (slot >= 0) ? *reinterpret_cast<const double2 *>(rowc + slot) : make_double2(0.0, 0.0);
-        }
+      for (int it = 0; it < kIt; ++it) {
+        const int q = qb + 8 * it;
+        const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
+        v[it] = (slot >= 0) ? *reinterpret_cast<const double2 *>(rowc + slot) : make_double2(0.0, 0.0);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int c = c0 + cc + 8 * u;
-#pragma unroll
-        for (int it = 0; it < kIt; ++it) {
-          const int q = lane + 32 * it;
-          if (q < r32) {
-            double y = 0.0;
-            if (q < r && c < n) {
-              const double *h = sh + 6 * q;
-              y = h[0] * p[u][0] + h[1] * p[u][1] + h[2] * p[u][2];
-              if (h[5] >= 0.0) y += h[3] * v[u][it].x + h[4] * v[u][it].y;
-            }
-            Y[q * kW3YS + cc + 8 * u] = y;
+      for (int it = 0; it < kIt; ++it) {
+        const int q = qb + 8 * it;
+        if (q < r32) {
+          double y = 0.0;
+          if (q < r && live) {
+            const double *h = sh + 6 * q;
+            y = h[0] * p0 + h[1] * p1 + h[2] * p2;
+            if (h[5] >= 0.0) y += h[3] * v[it].x + h[4] * v[it].y;
           }
+          Y[q * kW3YS + lane] = y;
         }
       }
     }
-    for (int q = 256 + tid; q < r32; q += 256)        // rows beyond kIt·32 (only if r > 256): plain path
-      for (int cc = 0; cc < kW3Cols; ++cc) {
-        const int c = c0 + cc;
-        double y = 0.0;
-        if (q < r && c < n) {
-          const double *rowc = Sg + (size_t)c * ld, *h = sh + 6 * q;
-          y = h[0] * rowc[0] + h[1] * rowc[1] + h[2] * rowc[2];
-          if (h[5] >= 0.0) y += h[3] * rowc[(int)h[5]] + h[4] * rowc[(int)h[5] + 1];
-        }
-        Y[q * kW3YS + cc] = y;
-      }
     __syncthreads();                                  // sh (aliasing Lp) is dead from here on
   }
   REKF_WSTAMP();
@@ -138,13 +123,19 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       cp8(Xs + i * 32 + (k ^ swz(i)), Dg + e);
     }
   };
-  auto stage_L = [&](int Js, int i0s, double *buf) {   // rows i0s.. of panel Js (always a full 32-column panel)
+  // rows i0s.. of panel Js (always a full 32-column panel), k-major like L's own column-major storage: 16-byte copies
+  auto stage_L = [&](int Js, int i0s, double *buf) {
     const int nr = min(kW3Chunk, r - i0s);
-    for (int e = tid; e < kW3Chunk * 32; e += 256) {
-      const int ii = e & (kW3Chunk - 1), k = e >> 6;
-      double *dst = buf + ii * 32 + (k ^ swz(ii));
-      if (ii < nr) cp8(dst, Sb + (size_t)(Js + k) * sld + i0s + ii);
-      else *dst = 0.0;
+    for (int e = tid; e < 32 * (kW3Chunk / 2); e += 256) {
+      const int k = e >> 5, ii = (e & 31) * 2;
+      double *dst = buf + k * kW3LP + ii;
+      const double *src = Sb + (size_t)(Js + k) * sld + i0s + ii;
+      if (ii + 1 < nr) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+      } else {
+        dst[0] = (ii < nr) ? src[0] : 0.0;
+        dst[1] = 0.0;
+      }
     }
   };
   int cur = 0;                                        // chunk buffer holding the stage about to be consumed
@@ -193,11 +184,11 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
         int Jn = J, in = i0 + kW3Chunk;
         if (in >= r) { Jn = J + kCholNb; in = Jn + kCholNb; }
         if (in < r) {
-          stage_L(Jn, in, Lp + (cur ^ 1) * kW3Chunk * 32);
+          stage_L(Jn, in, Lp + (cur ^ 1) * 32 * kW3LP);
           asm volatile("cp.async.commit_group;" ::: "memory");
         }
       }
-      const double *Lc = Lp + cur * kW3Chunk * 32;
+      const double *Lc = Lp + cur * 32 * kW3LP;
       const int ntile = (nrows + 7) >> 3;
       // this warp's (up to) four row tiles of the chunk as four independent DMMA chains
       double d0[4], d1[4];
@@ -212,7 +203,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int li = 8 * (rp + 2 * q) + g;
-          dmma884(d0[q], d1[q], -Lc[li * 32 + ((4 * ks + t4) ^ swz(li))], wb[ks], d0[q], d1[q]);
+          dmma884(d0[q], d1[q], -Lc[(4 * ks + t4) * kW3LP + li], wb[ks], d0[q], d1[q]);
         }
       }
 #pragma unroll
