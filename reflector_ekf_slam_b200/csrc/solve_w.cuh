@@ -24,7 +24,7 @@ constexpr int kW3Chunk = 64;             // rows of L staged per pass
 constexpr int kW3LP = kW3Chunk + 4;      // pitch of a staged L chunk, k-major [32 k][68]: A-fragment loads conflict free
 
 inline size_t smem_solve_w3(int rld) {
-  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * 32 * kW3LP + 32 * 32 + rld) + 64 * sizeof(int);
+  return sizeof(double) * ((size_t)(rld + 8) * kW3YS + (size_t)2 * 32 * kW3LP + 32 * 32 + rld + 32) + 64 * sizeof(int);
 }
 
 // column swizzle of the 32-wide operand tiles: conflict-free both for row-contiguous staging stores and for the
@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   double *Xs = Lp + 2 * 32 * kW3LP;                   // [32][32] swizzled inverse of the current diagonal block
   double *nu = Xs + 32 * 32;                          // [rld] L⁻¹ν (row r of the factor), staged once
   int *sexp = reinterpret_cast<int *>(nu + rld);      // [32]
+  double *sdiag = reinterpret_cast<double *>(sexp + 64);   // [32] prior Σ[c][c] of this CTA's columns, fetched up front
+  if (threadIdx.x < kW3Cols) sdiag[threadIdx.x] = Sg[(size_t)min(c0 + (int)threadIdx.x, ld - 1) * (ld + 1)];
   for (int k = threadIdx.x; k < r; k += 256) nu[k] = Sb[(size_t)k * sld + r];   // visible after the gather's barriers
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;             // DMMA fragment coordinates
@@ -62,6 +64,11 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
 #define REKF_WSTAMP() do { if (tid == 0 && blockIdx.x == 0) tlog[tl++] = (double)clock64(); } while (0)
 #else
 #define REKF_WSTAMP() do { } while (0)
+#endif
+#ifdef REKF_SOLVE_TIMING2
+#define REKF_WSTAMP2() REKF_WSTAMP()
+#else
+#define REKF_WSTAMP2() do { } while (0)
 #endif
   REKF_WSTAMP();
 
@@ -76,20 +83,24 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       sh[6 * q + 5] = (double)Hslot[q];
     }
     __syncthreads();
+    REKF_WSTAMP2();
     // lane = column (its Σ row and pose entries stay in registers), warps stride the measurement rows: the row
     // descriptor is one broadcast read, the Y store is conflict free, eight Σ reads are in flight per lane
+    // Σ is bit-exactly symmetric, so Σ[b][c] is read as row b, columns c0..c0+31: every access of the gather is a
+    // coalesced 256-byte segment (reading row c at scattered slots would cost one 32-byte sector per element)
     const int c = c0 + lane;
     const bool live = c < n;
-    const double *rowc = Sg + (size_t)min(c, n - 1) * ld;
-    const double p0 = rowc[0], p1 = rowc[1], p2 = rowc[2];
-    constexpr int kIt = 8;
+    const int cl = min(c, ld - 1);
+    const double p0 = Sg[cl], p1 = Sg[(size_t)ld + cl], p2 = Sg[(size_t)2 * ld + cl];
+    constexpr int kIt = 14;                           // 28 Σ reads in flight per lane: two rounds at r = 200
     for (int qb = warp; qb < r32; qb += 8 * kIt) {
-      double2 v[kIt];
+      double va[kIt], vb[kIt];
 #pragma unroll
       for (int it = 0; it < kIt; ++it) {
         const int q = qb + 8 * it;
         const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
-        v[it] = (slot >= 0) ? *reinterpret_cast<const double2 *>(rowc + slot) : make_double2(0.0, 0.0);
+        va[it] = (slot >= 0) ? Sg[(size_t)slot * ld + cl] : 0.0;
+        vb[it] = (slot >= 0) ? Sg[(size_t)(slot + 1) * ld + cl] : 0.0;
       }
 #pragma unroll
       for (int it = 0; it < kIt; ++it) {
@@ -99,12 +110,13 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
           if (q < r && live) {
             const double *h = sh + 6 * q;
             y = h[0] * p0 + h[1] * p1 + h[2] * p2;
-            if (h[5] >= 0.0) y += h[3] * v[it].x + h[4] * v[it].y;
+            if (h[5] >= 0.0) y += h[3] * va[it] + h[4] * vb[it];
           }
           Y[q * kW3YS + lane] = y;
         }
       }
     }
+    REKF_WSTAMP2();
     __syncthreads();                                  // sh (aliasing Lp) is dead from here on
   }
   REKF_WSTAMP();
@@ -148,17 +160,21 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     __syncthreads();                                  // X_J landed; also orders the gather / previous trailing update
     REKF_WSTAMP();
     // W_J = X_J·Y_J : 4 row tiles x 4 column tiles of 8x8; this warp: column tile nt, row tiles rp and rp+2
-    double w0[2], w1[2];
-    w0[0] = w0[1] = w1[0] = w1[1] = 0.0;
+    double w0[2], w1[2], u0[2], u1[2];
+    w0[0] = w0[1] = w1[0] = w1[1] = u0[0] = u0[1] = u1[0] = u1[1] = 0.0;
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {                  // two independent chains; X is zero above its diagonal
+    for (int ks = 0; ks < 4; ++ks) {                  // four independent chains; X is zero above its diagonal
       const double b = Y[(J + 4 * ks + t4) * kW3YS + 8 * nt + g];
+      const double b2 = Y[(J + 4 * (ks + 4) + t4) * kW3YS + 8 * nt + g];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int xi = 8 * (rp + 2 * h) + g;
         dmma884(w0[h], w1[h], Xs[xi * 32 + ((4 * ks + t4) ^ swz(xi))], b, w0[h], w1[h]);
+        dmma884(u0[h], u1[h], Xs[xi * 32 + ((4 * (ks + 4) + t4) ^ swz(xi))], b2, u0[h], u1[h]);
       }
     }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) { w0[h] += u0[h]; w1[h] += u1[h]; }
     __syncthreads();                                  // every warp has read Y_J and X_J
     if (J + kCholNb < r) {                            // X of the next block: lands during this block's trailing update
       stage_X(J + kCholNb);
@@ -198,14 +214,20 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
         const double2 cv = *reinterpret_cast<const double2 *>(Y + min(i0 + 8 * rt + g, rld + 7) * kW3YS + 8 * nt + 2 * t4);
         d0[q] = cv.x; d1[q] = cv.y;
       }
+      double e0[4], e1[4];                            // second half of K as its own chain: half the dependent depth
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
+      for (int q = 0; q < 4; ++q) e0[q] = e1[q] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int li = 8 * (rp + 2 * q) + g;
           dmma884(d0[q], d1[q], -Lc[(4 * ks + t4) * kW3LP + li], wb[ks], d0[q], d1[q]);
+          dmma884(e0[q], e1[q], -Lc[(4 * (ks + 4) + t4) * kW3LP + li], wb[ks + 4], e0[q], e1[q]);
         }
       }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { d0[q] += e0[q]; d1[q] += e1[q]; }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int rt = rp + 2 * q;
@@ -220,51 +242,56 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
 
   // ---- μ += Wᵀ·(L⁻¹ν) (:306), θ wrapped (:307); exact diagonal of the downdate -------------------------------
   double *mu = L.mu + (size_t)s * ld;
-  for (int cc = warp; cc < kW3Cols; cc += 8) {
-    const int c = c0 + cc;
+  double *red = Lp;                                   // [3][8][32] partial sums (the L chunk buffers are dead)
+  {                                                   // lane = column, warps stride the rows: conflict-free reads
     double a = 0.0, d2 = 0.0, mx = 0.0;
-    for (int k = lane; k < r; k += 32) {
-      const double wv = Y[k * kW3YS + cc];
+    for (int k = warp; k < r; k += 8) {
+      const double wv = Y[k * kW3YS + lane];
       a = fma(wv, nu[k], a);
       d2 = fma(wv, wv, d2);
       mx = fmax(mx, fabs(wv));
     }
+    red[warp * 32 + lane] = a;
+    red[(8 + warp) * 32 + lane] = d2;
+    red[(16 + warp) * 32 + lane] = mx;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int cc = lane, c = c0 + cc;
+    double a = 0.0, d2 = 0.0, mx = 0.0;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, off);
-      d2 += __shfl_xor_sync(0xffffffffu, d2, off);
-      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    for (int w = 0; w < 8; ++w) {
+      a += red[w * 32 + cc];
+      d2 += red[(8 + w) * 32 + cc];
+      mx = fmax(mx, red[(16 + w) * 32 + cc]);
     }
-    if (lane == 0) {
-      if (c < n) {
-        const double v = mu[c] + a;
-        mu[c] = (c == 2) ? wrap_angle(v) : v;
-      }
-      // The diagonal of the downdate is a sum of squares: every truncation of a tensor-core product has
-      // the same sign there and would accumulate step after step, so it is kept in fp64.
-      if (L.Wdiag) L.Wdiag[(size_t)s * ld + c] = (c < n) ? d2 : 0.0;
-      if (L.Wq) {
-        const int e = (mx > 0.0 && c < n) ? ilogb(mx) + 2 : 0;
-        sexp[cc] = e;
-        L.Wexp[(size_t)s * ld + c] = e;
-        L.Wscale[(size_t)s * ld + c] = scalbn(1.0, e);
-        // int8 slices resolve 2^-29 of the row scale 2^e; when the downdate removes almost all of a state's
-        // variance that is no longer small against the posterior → this frame takes the fp64 SYRK.
-        // Such slots are flagged: the tensor kernel skips their rows/columns and k_syrk_exact_rows does them in
-        // fp64.  More than kMaxExactSlots of them (first update after map building: everything collapses) and the
-        // whole frame goes to the fp64 SYRK.
-        bool exact = false;
-        if (mx > 0.0 && c < n) {
-          const double post = Sg[(size_t)c * ld + c] - d2;
-          exact = !(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post;
-          if (exact) {
-            const int pos = atomicAdd(&L.st[s].exact_slots, 1);
-            if (pos < kMaxExactSlots) L.exact_list[(size_t)s * kMaxExactSlots + pos] = c;
-            else atomicOr(&L.st[s].exact_update, 1);
-          }
+    if (c < n) {
+      const double v = mu[c] + a;
+      mu[c] = (c == 2) ? wrap_angle(v) : v;
+    }
+    // The diagonal of the downdate is a sum of squares: every truncation of a tensor-core product has
+    // the same sign there and would accumulate step after step, so it is kept in fp64.
+    if (L.Wdiag) L.Wdiag[(size_t)s * ld + c] = (c < n) ? d2 : 0.0;
+    if (L.Wq) {
+      const int e = (mx > 0.0 && c < n) ? ilogb(mx) + 2 : 0;
+      sexp[cc] = e;
+      L.Wexp[(size_t)s * ld + c] = e;
+      L.Wscale[(size_t)s * ld + c] = scalbn(1.0, e);
+      // int8 slices resolve 2^-29 of the row scale 2^e; when the downdate removes almost all of a state's
+      // variance that is no longer small against the posterior, so such slots are flagged: the tensor kernel
+      // skips their rows/columns and k_syrk_exact_rows does them in fp64.  More than kMaxExactSlots of them
+      // (first update after map building: everything collapses) and the whole frame goes to the fp64 SYRK.
+      bool exact = false;
+      if (mx > 0.0 && c < n) {
+        const double post = sdiag[cc] - d2;
+        exact = !(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post;
+        if (exact) {
+          const int pos = atomicAdd(&L.st[s].exact_slots, 1);
+          if (pos < kMaxExactSlots) L.exact_list[(size_t)s * kMaxExactSlots + pos] = c;
+          else atomicOr(&L.st[s].exact_update, 1);
         }
-        L.Wflag[(size_t)s * ld + c] = exact ? 1 : 0;
       }
+      L.Wflag[(size_t)s * ld + c] = exact ? 1 : 0;
     }
   }
   __syncthreads();
@@ -272,36 +299,54 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
 
   // ---- operand panels of Wᵀ (row c, K contiguous), zero beyond r ---------------------------------------------------
   if (L.W64) {
-    double *W = L.W64 + (size_t)s * ld * rld;
-    for (int e = tid; e < kW3Cols * rld; e += 256) {
-      const int cc = e / rld, k = e - cc * rld;
-      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kW3YS + cc] : 0.0;
-    }
+    // 8 rows x 4 columns per warp step: the shared-memory reads are conflict free and every column's 8 values
+    // are two full 32-byte sectors of its W row
+    const int kk = (lane & 3) | ((lane >> 4) << 2), cc = 4 * warp + ((lane >> 2) & 3);
+    double *Wr = L.W64 + (size_t)s * ld * rld + (size_t)(c0 + cc) * rld;
+    for (int k = kk; k < rld; k += 8) Wr[k] = (k < r) ? Y[k * kW3YS + cc] : 0.0;
   }
+  REKF_WSTAMP2();
   if (L.Wq) {
-    // x = w·2^-e, |x| <= 1/2, x ≈ Σ_p d_p·2^(-7(p+1)); d_p = rint(·) by magic-number addition (exact, no cvt / libm)
+    // x = w·2^-e, |x| < 1/2, x ≈ Σ_p d_p·2^(-7(p+1)).  q = rint(w·2^(28-e)) by magic-number addition (one fp64 FMA,
+    // |q| <= 2^27), then four balanced base-128 digits d_p ∈ [-64, 64] by integer arithmetic: q = Σ d_p·128^(3-p)
     const double kMagic = 6755399441055744.0;          // 2^52 + 2^51
+    constexpr int kQP = 68;                            // words per staged row: 64 K-groups of 4, 16-byte aligned rows
+    uint32_t *Qs = reinterpret_cast<uint32_t *>(Lp);   // [4 planes][32 columns][kQP]
     const int kq4 = L.kq / 4;
-    for (int e4 = tid; e4 < kW3Cols * kq4; e4 += 256) {
-      const int cc = e4 / kq4, k0 = (e4 - cc * kq4) * 4;
-      const bool live = (c0 + cc < n);
-      const double sc = __longlong_as_double((long long)(1023 + 7 - sexp[cc]) << 52);   // 2^(7-e)
-      uint32_t packed[4] = {0u, 0u, 0u, 0u};
+    const bool live = (c0 + lane < n);
+    const double sc = __longlong_as_double((long long)(1023 + 28 - sexp[lane]) << 52);  // 2^(28-e)
+    for (int g0 = 0; g0 < kq4; g0 += 64) {             // 256 K values per pass
+      const int ng = min(64, kq4 - g0);
+      for (int kg = warp; kg < ng; kg += 8) {
+        const int k0 = (g0 + kg) * 4;
+        uint32_t packed[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + u;
-        double rem = (live && k < r) ? Y[k * kW3YS + cc] * sc : 0.0;
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + u;
+          const double wv = (live && k < r) ? Y[k * kW3YS + lane] : 0.0;
+          int q = __double2loint(fma(wv, sc, kMagic));
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const double t = rem + kMagic;
-          const double d = t - kMagic;                 // rint(rem)
-          packed[p] |= ((uint32_t)__double2loint(t) & 0xffu) << (8 * u);
-          rem = (rem - d) * 128.0;
+          for (int p = 3; p > 0; --p) {
+            const int d = ((q + 64) & 127) - 64;
+            packed[p] |= ((uint32_t)d & 0xffu) << (8 * u);
+            q = (q - d) >> 7;
+          }
+          packed[0] |= ((uint32_t)q & 0xffu) << (8 * u);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) Qs[(p * 32 + lane) * kQP + kg] = packed[p];
+      }
+      __syncthreads();
+      REKF_WSTAMP2();
+      for (int e = tid; e < 128 * 16; e += 256) {      // row = plane * 32 + column, 16 bytes per thread
+        const int row = e >> 4, j = (e & 15) * 4;
+        if (j < ng) {                                  // kq is a multiple of 64 bytes: ng is a multiple of 16 words
+          const int p = row >> 5, cc = row & 31;
+          uint32_t *dst = reinterpret_cast<uint32_t *>(L.Wq + (((size_t)s * 4 + p) * ld + c0 + cc) * L.kq) + g0 + j;
+          *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(Qs + row * kQP + j);
         }
       }
-#pragma unroll
-      for (int p = 0; p < 4; ++p)
-        *reinterpret_cast<uint32_t *>(L.Wq + (((size_t)s * 4 + p) * ld + c0 + cc) * L.kq + k0) = packed[p];
+      if (g0 + 64 < kq4) __syncthreads();
     }
   } else if (L.Wt_hi) {
     float *Wh = L.Wt_hi + (size_t)s * ld * rld, *Wl = L.Wt_lo + (size_t)s * ld * rld;
