@@ -44,6 +44,7 @@ struct rekf_handle {
   bool own_stream = false;
   std::string err;
   int64_t launches = 0;
+  int64_t step_launches = 0;   // kernel nodes in the captured step graph
   // device mailbox for host-delivered messages + pinned staging ring
   char *mb_dev = nullptr;
   char *mb_host = nullptr;
@@ -195,8 +196,9 @@ int launch_observation(rekf_handle *h, const InputRef &in) {
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
       k_syrk_f64<<<dim3(592, 1, L.S), 256, 0, h->stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
-      k_syrk_f64<<<dim3(148, 1, L.S), 256, 0, h->stream>>>(L);   // exits at once unless st.exact_update
-      k_syrk_exact_rows<<<dim3((L.ncap + 7) / 8, 8, L.S), 256, 0, h->stream>>>(L);   // fp64 rows/columns of flagged slots
+      // fp64 side of the hybrid: the whole frame if st.exact_update, else the rows/columns of flagged slots, else nothing
+      k_syrk_f64<<<dim3(148, 1, L.S), 256, 0, h->stream>>>(L);
+      ++h->launches;                                              // two kernels inside this scope
       int rc = h->persistent_syrk ? syrk_i8p_launch(h->tc8p, L, h->stream) : syrk_i8_launch(h->tc8, L, h->stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
@@ -527,6 +529,7 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     if (!same) {
       if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
       cudaGraph_t g = nullptr;
+      const int64_t before = h->launches;
       CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
       int rc = launch_odometry(h, in);
       if (!rc) rc = launch_observation(h, in);
@@ -537,10 +540,11 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
       CK(cudaGraphInstantiate(&h->step_graph, g, 0));
       cudaGraphDestroy(g);
       h->graph_in = in;
-      h->launches -= K_COUNT;   // the capture pass itself launched nothing
+      h->step_launches = h->launches - before;   // kernel nodes per step
+      h->launches = before;                      // the capture pass itself launched nothing
     }
     for (int t = 0; t < T; ++t) CK(cudaGraphLaunch(h->step_graph, h->stream));
-    h->launches += (int64_t)T * K_COUNT;
+    h->launches += (int64_t)T * h->step_launches;
     return REKF_OK;
   }
   for (int t = 0; t < T; ++t) {

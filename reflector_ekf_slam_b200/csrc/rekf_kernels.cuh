@@ -15,6 +15,7 @@
 // of five rows of Σ per measurement row and is never materialised outside shared memory.
 #pragma once
 #include "rekf_device.cuh"
+#include "syrk_exact_rows.cuh"
 
 namespace rekf {
 
@@ -681,7 +682,10 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
   const SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
-  if (L.Wq && !st.exact_update) return;     // int8 tensor-core SYRK handles this frame
+  if (L.Wq && !st.exact_update) {           // the int8 tensor-core SYRK handles this frame, except flagged slots
+    syrk_exact_rows(L, s);
+    return;
+  }
   const int n = internal_dim(st.N);
   const int Tn = L.ld / 64;
   for (int tile = blockIdx.x; tile < Tn * Tn; tile += gridDim.x) {   // grid-stride over tiles: a cheap no-op launch

@@ -13,34 +13,35 @@
 
 namespace rekf {
 
-__global__ void __launch_bounds__(256) k_syrk_exact_rows(Layout L) {
-  const int s = blockIdx.z;
+// Called by every CTA of k_syrk_f64's (148, 1, S) launch in int8 mode: warps stride the columns, so a frame
+// without flagged slots costs one read of SessionState per CTA and no second launch.
+__device__ __forceinline__ void syrk_exact_rows(const Layout &L, int s) {
   const SessionState &st = L.st[s];
   const int r = st.r;
   const int cnt = min(st.exact_slots, kMaxExactSlots);
   if (r == 0 || cnt == 0 || st.exact_update) return;       // exact_update: the whole frame is done by k_syrk_f64
   const int n = internal_dim(st.N);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int j = blockIdx.x * 8 + warp;                      // column handled by this warp
-  if (j >= n) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int ld = L.ld, rld = L.rld;
   const double *W = L.W64 + (size_t)s * ld * rld;
   const unsigned char *flag = L.Wflag + (size_t)s * ld;
   const int *list = L.exact_list + (size_t)s * kMaxExactSlots;
   double *Sg = L.sigma + (size_t)s * ld * ld;
-  const double *wj = W + (size_t)j * rld;
-  for (int q = blockIdx.y; q < cnt; q += gridDim.y) {
-    const int a = list[q];
-    if (flag[j] && j < a) continue;                         // (j, a) is owned by row j
-    const double *wa = W + (size_t)a * rld;
-    double acc = 0.0;
-    for (int k = lane; k < r; k += 32) acc = fma(wa[k], wj[k], acc);
+  for (int j = blockIdx.x * nwarp + warp; j < n; j += gridDim.x * nwarp) {   // column handled by this warp
+    const double *wj = W + (size_t)j * rld;
+    for (int q = 0; q < cnt; ++q) {
+      const int a = list[q];
+      if (flag[j] && j < a) continue;                       // (j, a) is owned by row j
+      const double *wa = W + (size_t)a * rld;
+      double acc = 0.0;
+      for (int k = lane; k < r; k += 32) acc = fma(wa[k], wj[k], acc);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-      const double v = Sg[(size_t)a * ld + j] - acc;
-      Sg[(size_t)a * ld + j] = v;
-      Sg[(size_t)j * ld + a] = v;
+      for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+      if (lane == 0) {
+        const double v = Sg[(size_t)a * ld + j] - acc;
+        Sg[(size_t)a * ld + j] = v;
+        Sg[(size_t)j * ld + a] = v;
+      }
     }
   }
 }

@@ -3,8 +3,8 @@
 // digit-slice scheme).  What changes is the data movement, because the kernel is HBM-bound:
 //
 //   * one CTA per SM loops over (session, tile) work items: 128x64 tiles on/above the diagonal;
-//   * Σ tiles travel by TMA in both directions: two 128-row x 32-column half-tiles (4 boxes of 16 columns, 128-byte
-//     swizzle) are double-buffered in shared memory — full-line HBM reads issued a whole tile ahead, full-line
+//   * Σ tiles travel by TMA in both directions: 128-row x 32-column half-tiles (2 boxes of 16 columns, 128-byte
+//     swizzle) in a four-slot shared-memory ring (two whole tiles) — full-line HBM reads issued a whole tile ahead, full-line
 //     writes, no partial sectors, no L1 thrash; only the mirrored lower-triangle copy is written from registers
 //     (coalesced across lanes);
 //   * the s32 accumulators are double-buffered in TMEM (2 x 4 x 64 columns = all 512), so the tensor pipe works on
@@ -20,7 +20,10 @@ namespace rekf {
 
 constexpr int kPThreads = 384;                           // 12 warps: 8 epilogue, operand TMA, MMA, Σ load, Σ store
 constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ: 128 rows x 32 columns fp64 = 32 KB
-constexpr int kPSmemBytes = kI8Stages * kI8StageBytes + 2 * kPSigHalf + 1024 + 256;
+constexpr int kPSigSlots = 4;                            // Σ half-tile ring: two whole tiles, so loads run a full tile ahead
+constexpr int kPMaxSess = 64;                           // sessions whose (r, n) are cached in shared memory
+// operand ring + Σ ring + alignment slack + barriers + [2][64] column scales + [2][64] column flags + session table
+constexpr int kPSmemBytes = kI8Stages * kI8StageBytes + kPSigSlots * kPSigHalf + 1024 + 256 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8;
 
 struct SyrkI8P {
   CUtensorMap map_a, map_b, map_sig;
@@ -61,11 +64,21 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *ops = base;                                   // [2][48 KB] int8 slice boxes
-  uint8_t *sig = base + kI8Stages * kI8StageBytes;       // [2][32 KB] Σ half-tiles
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sig + 2 * kPSigHalf);
+  uint8_t *sig = base + kI8Stages * kI8StageBytes;       // [4][32 KB] Σ half-tiles
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sig + kPSigSlots * kPSigHalf);
   uint64_t *op_full = bars, *op_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6, *sig_full = bars + 8,
-           *sig_empty = bars + 10, *sig_done = bars + 12;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14);
+           *sig_empty = bars + 12, *sig_done = bars + 16;
+  uint64_t *sc_full = bars + 20;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 22);
+  double *sc_tab = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [2][64] Wscale of the tile's columns
+  unsigned char *fl_tab = reinterpret_cast<unsigned char *>(sc_tab + 2 * 64);             // [2][64] Wflag of the tile's columns
+  int *sess_r = reinterpret_cast<int *>(fl_tab + 2 * 64);                                  // [kPMaxSess] r, 0 = nothing to do
+  int *sess_n = sess_r + kPMaxSess;                                                        // [kPMaxSess] internal dimension
+  for (int q = threadIdx.x; q < min(L.S, kPMaxSess); q += kPThreads) {
+    const SessionState &st = L.st[q];
+    sess_r[q] = (st.r > 0 && !st.exact_update) ? st.r : 0;
+    sess_n[q] = internal_dim(st.N);
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tn64 = L.ld / kI8TileN;
@@ -76,7 +89,9 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&op_full[i], 1); mbar_init(&op_empty[i], 1);
-        mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256);
+        mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); mbar_init(&sc_full[i], 1);
+      }
+      for (int i = 0; i < kPSigSlots; ++i) {
         mbar_init(&sig_full[i], 1); mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], 256);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -99,9 +114,13 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     const int tj = 2 * ti + rem;
     i0 = ti * 128; j0 = tj * kI8TileN;
     inA = rem < 2;
-    const SessionState &st = L.st[s];
-    r = st.r; n = internal_dim(st.N);
-    return r > 0 && !st.exact_update && j0 < n;
+    if (s < kPMaxSess) {
+      r = sess_r[s]; n = sess_n[s];
+    } else {
+      const SessionState &st = L.st[s];
+      r = (st.r > 0 && !st.exact_update) ? st.r : 0; n = internal_dim(st.N);
+    }
+    return r > 0 && j0 < n;
   };
 
   if (warp == 8) {
@@ -165,21 +184,38 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       }
     }
   } else if (warp == 10) {
-    // ===== Σ-tile TMA loader (tiles strictly above the diagonal) =====
-    if (lane == 0) {
-      uint32_t sit = 0;
-      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
-        int s, i0, j0, r, n; bool inA;
-        if (!decode(item, s, i0, j0, r, n, inA) || inA) continue;
-        for (int h = 0; h < 2; ++h) {
-          if (!mbar_wait_backoff(&sig_empty[h], (sit & 1) ^ 1)) { timeout = true; break; }
-          uint8_t *dst = sig + (size_t)h * kPSigHalf;
-          mbar_expect_tx(&sig_full[h], kPSigHalf);
-          tma_load_3d(dst, &map_sig, &sig_full[h], j0 + 32 * h, i0, s);
-          tma_load_3d(dst + kPSigHalf / 2, &map_sig, &sig_full[h], j0 + 32 * h + 16, i0, s);
-        }
-        ++sit;
+    // ===== column scales / flags of every tile → shared memory (whole warp); Σ-tile TMA loads (lane 0, tiles strictly
+    //       above the diagonal).  The scale slot is the accumulator set's: free once the epilogue released that set. =====
+    uint32_t sit = 0, iter = 0;
+    for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+      int s, i0, j0, r, n; bool inA;
+      if (!decode(item, s, i0, j0, r, n, inA)) continue;
+      const int set = iter & 1;
+      if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
+      {
+        const size_t off = (size_t)s * L.ld + j0 + 2 * lane;
+        const double2 v = *reinterpret_cast<const double2 *>(L.Wscale + off);
+        const unsigned short f = *reinterpret_cast<const unsigned short *>(L.Wflag + off);
+        *reinterpret_cast<double2 *>(sc_tab + set * 64 + 2 * lane) = v;
+        *reinterpret_cast<unsigned short *>(fl_tab + set * 64 + 2 * lane) = f;
       }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sc_full[set]);
+        if (!inA) {
+          for (int h = 0; h < 2; ++h) {
+            const int slot = ((sit & 1) << 1) | h;
+            if (!mbar_wait_backoff(&sig_empty[slot], ((sit >> 1) & 1) ^ 1)) { timeout = true; break; }
+            uint8_t *dst = sig + (size_t)slot * kPSigHalf;
+            mbar_expect_tx(&sig_full[slot], kPSigHalf);
+            tma_load_3d(dst, &map_sig, &sig_full[slot], j0 + 32 * h, i0, s);
+            tma_load_3d(dst + kPSigHalf / 2, &map_sig, &sig_full[slot], j0 + 32 * h + 16, i0, s);
+          }
+        }
+      }
+      timeout = __shfl_sync(0xffffffffu, (int)timeout, 0) != 0;
+      ++iter;
+      if (!inA) ++sit;
     }
   } else if (warp == 11) {
     // ===== Σ-tile TMA store: waits until the 256 epilogue threads have rewritten a half-tile, stores it, frees it =====
@@ -189,13 +225,14 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         int s, i0, j0, r, n; bool inA;
         if (!decode(item, s, i0, j0, r, n, inA) || inA) continue;
         for (int h = 0; h < 2; ++h) {
-          if (!mbar_wait_backoff(&sig_done[h], sit & 1)) { timeout = true; break; }
-          const uint8_t *src = sig + (size_t)h * kPSigHalf;
+          const int slot = ((sit & 1) << 1) | h;
+          if (!mbar_wait_backoff(&sig_done[slot], (sit >> 1) & 1)) { timeout = true; break; }
+          const uint8_t *src = sig + (size_t)slot * kPSigHalf;
           tma_store_3d(&map_sig, src, j0 + 32 * h, i0, s);
           tma_store_3d(&map_sig, src + kPSigHalf / 2, j0 + 32 * h + 16, i0, s);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(&sig_empty[h]);
+          mbar_arrive(&sig_empty[slot]);
         }
         ++sit;
       }
@@ -207,16 +244,23 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     const int il = quad * 32 + lane;                     // row inside the tile
     uint32_t iter = 0, sit = 0;
     const int ld = L.ld;
+    int row_s = -1, row_i0 = -1;                         // row scale / flag are reloaded only when the row block changes
+    double si = 0.0;
+    bool row_ok = false;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       int s, i0, j0, r, n; bool inA;
       if (!decode(item, s, i0, j0, r, n, inA)) continue;
       const int set = iter & 1;
       const int i = i0 + il;
       double *Sg = L.sigma + (size_t)s * ld * ld;
-      const double *Wsc = L.Wscale + (size_t)s * ld;
-      const unsigned char *flag = L.Wflag + (size_t)s * ld;
-      const double si = Wsc[min(i, ld - 1)] * 0x1p-35;
-      const bool row_ok = !flag[min(i, ld - 1)];
+      if (s != row_s || i0 != row_i0) {
+        si = L.Wscale[(size_t)s * ld + i] * 0x1p-35;
+        row_ok = !L.Wflag[(size_t)s * ld + i];
+        row_s = s; row_i0 = i0;
+      }
+      const double *sct = sc_tab + set * 64;
+      const unsigned char *flt = fl_tab + set * 64;
+      if (!mbar_wait(&sc_full[set], (iter >> 1) & 1)) timeout = true;
       if (!mbar_wait(&acc_full[set], (iter >> 1) & 1)) timeout = true;
       tc_fence_after();
 #pragma unroll 1
@@ -224,33 +268,31 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         const int col0 = 32 * h + 16 * halfw;            // first of this thread's 16 tile columns
         const int jbase = j0 + col0;
         const uint32_t taddr = tmem + set * 256 + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
+        // s32 accumulators of the four digit groups, two loads in flight; groups are recombined pairwise in 32 bits
+        // (|acc| < 2^23 for K <= 512, so acc·2^7 + acc' fits), then once in 64 bits: G = Σ_g acc_g · 2^(7·(3-g))
         long long G[16];
         {
-          uint32_t gq[16];
-          tc_ld16(taddr, gq);
+          uint32_t ga[16], gb[16];
+          int hi[16];
+          tc_ld16(taddr, ga);
+          tc_ld16(taddr + kI8TileN, gb);
           tc_wait_ld();
 #pragma unroll
-          for (int u = 0; u < 16; ++u) G[u] = (long long)(int)gq[u] << 21;
-          tc_ld16(taddr + kI8TileN, gq);
+          for (int u = 0; u < 16; ++u) hi[u] = ((int)ga[u] << 7) + (int)gb[u];
+          tc_ld16(taddr + 2 * kI8TileN, ga);
+          tc_ld16(taddr + 3 * kI8TileN, gb);
           tc_wait_ld();
 #pragma unroll
-          for (int u = 0; u < 16; ++u) G[u] += (long long)(int)gq[u] << 14;
-          tc_ld16(taddr + 2 * kI8TileN, gq);
-          tc_wait_ld();
-#pragma unroll
-          for (int u = 0; u < 16; ++u) G[u] += (long long)(int)gq[u] << 7;
-          tc_ld16(taddr + 3 * kI8TileN, gq);
-          tc_wait_ld();
-#pragma unroll
-          for (int u = 0; u < 16; ++u) G[u] += (long long)(int)gq[u];
+          for (int u = 0; u < 16; ++u) G[u] = ((long long)hi[u] << 14) + (long long)(((int)ga[u] << 7) + (int)gb[u]);
         }
-        const uint4 cf = *reinterpret_cast<const uint4 *>(flag + min(jbase, ld - 16));
-        const double2 *scj = reinterpret_cast<const double2 *>(Wsc + min(jbase, ld - 16));
+        const uint4 cf = *reinterpret_cast<const uint4 *>(flt + col0);
+        const double2 *scj = reinterpret_cast<const double2 *>(sct + col0);
         double cur[16];
         if (!inA) {
           // ---- Σ half-tile staged by TMA: read own row (swizzled 16-byte chunks), update, write back, TMA store ----
-          if (!mbar_wait(&sig_full[h], sit & 1)) timeout = true;
-          uint8_t *rowp = sig + (size_t)h * kPSigHalf + (size_t)halfw * (kPSigHalf / 2) + (size_t)il * 128;
+          const int slot = ((sit & 1) << 1) | h;
+          if (!mbar_wait(&sig_full[slot], (sit >> 1) & 1)) timeout = true;
+          uint8_t *rowp = sig + (size_t)slot * kPSigHalf + (size_t)halfw * (kPSigHalf / 2) + (size_t)il * 128;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const double2 t = *reinterpret_cast<const double2 *>(rowp + ((c ^ (il & 7)) << 4));
@@ -268,7 +310,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
-              if (!((cfw >> (8 * (u & 3))) & 0xffu)) cur[u] = fma(-i64_to_f64(G[u]), si * Wsc[min(jbase + u, ld - 1)], cur[u]);
+              if (!((cfw >> (8 * (u & 3))) & 0xffu)) cur[u] = fma(-i64_to_f64(G[u]), si * sct[col0 + u], cur[u]);
             }
           }
 #pragma unroll
@@ -276,7 +318,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
             *reinterpret_cast<double2 *>(rowp + ((c ^ (il & 7)) << 4)) = make_double2(cur[2 * c], cur[2 * c + 1]);
           // mirrored lower-triangle copy straight from registers (lanes = consecutive rows: coalesced)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&sig_done[h]);                        // hand the half-tile to the store warp
+          mbar_arrive(&sig_done[slot]);                     // hand the half-tile to the store warp
           if (no_flags && i < n && jbase + 15 < n) {
 #pragma unroll
             for (int u = 0; u < 16; ++u) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
