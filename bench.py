@@ -38,6 +38,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--sessions", type=int, default=8, help="independent sessions per GPU")
+    ap.add_argument("--groups", type=int, default=2, help="pipeline groups the sessions of one GPU are split into (1: lock-step)")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent SYRK leaves to other groups (0: engine default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cov", default="i8", choices=["i8", "tcgen05", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,7 +227,9 @@ def run_b200(args):
     else:
         streams = build_streams(S, T + EXTRA)
 
-    batch = EKFBatch(S, max_landmarks=N_LM, max_observations=M_OBS, device=local, cov_update=cov, use_graphs=1)
+    G = max(1, min(args.groups, S))
+    batch = EKFBatch(S, max_landmarks=N_LM, max_observations=M_OBS, device=local, cov_update=cov, use_graphs=1,
+                     pipeline_groups=G, syrk_reserve_sms=args.reserve_sms)
     nb = warm_start(batch, streams)
 
     def dev_inputs(lo, hi):
@@ -306,20 +310,40 @@ def run_b200(args):
     batch.sync()
     if world > 1:
         dist.barrier()
+    # (3a) blocking form: the pose is read back (and waited for) after every step, like the node's GetState()
+    Kb = Ke // 2
     t0 = time.perf_counter()
-    for k in range(Ke):
+    for k in range(Kb):
         batch.handle_odometry(od[k])
         batch.handle_observation(ot[k], ox[k])
         batch.poses(poses)
+    e2e_block_s = time.perf_counter() - t0
+    # (3b) streaming form: every step's poses still come back to the host, through the pinned ring, but the host
+    # redeems a step's ticket LAG steps later, so the groups keep their stagger
+    LAG = 8
+    pending = []
+    t0 = time.perf_counter()
+    for k in range(Kb, Ke):
+        batch.handle_odometry(od[k])
+        batch.handle_observation(ot[k], ox[k])
+        pending.append(batch.request_poses())
+        if len(pending) > LAG:
+            batch.fetch_poses(pending.pop(0), poses)
+    for t in pending:
+        batch.fetch_poses(t, poses)
     e2e_s = time.perf_counter() - t0
+    Ke_stream = Ke - Kb
     if world > 1:
-        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        tmax = torch.tensor([e2e_s, e2e_block_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
-    e2e_value = world * S * Ke / e2e_s
+        e2e_s, e2e_block_s = float(tmax[0].item()), float(tmax[1].item())
+    e2e_value = world * S * Ke_stream / e2e_s
     h2d = S * (4 * 8) + S * (8 + 4 * 8 + 4) + S * M_OBS * 8
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": S * 24, "steps": Ke,
-           "api": "rekf_batch_handle_odometry + rekf_batch_handle_observation + rekf_batch_get_pose per step (host buffers)"}
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": S * 24, "steps": Ke_stream,
+           "api": "rekf_batch_handle_odometry + rekf_batch_handle_observation + rekf_batch_request_poses per step (host buffers in, "
+                  f"poses of every step out through the pinned ring, ticket redeemed {LAG} steps later)",
+           "blocking": {"value": world * S * Kb / e2e_block_s, "steps": Kb,
+                        "api": "same calls with rekf_batch_get_pose (host waits for the pose) after every step"}}
 
     # ---- (4) optional: one session alone (latency-bound single-stream figure) ----------------------------
     single = None
@@ -350,8 +374,8 @@ def run_b200(args):
                       2: "f64 state/solve + exact int8-slice (4x7-bit) tcgen05 covariance GEMM (s32 TMEM accumulate)"}[cov],
             "data": "synthetic",
             "config": {"workload": f"{CONFIG}: synthetic 2D stream, N={N_LM} landmarks, {M_OBS} observed/step, diff odom; "
-                                   f"{S} independent sessions per GPU in lock-step (BASELINE config 5 per-GPU slice)",
-                       "sessions_per_gpu": S, "n": n_ref, "r": r, "cov_update": args.cov,
+                                   f"{S} independent sessions per GPU (BASELINE config 5 per-GPU slice) in {G} pipeline group(s)",
+                       "sessions_per_gpu": S, "pipeline_groups": G, "n": n_ref, "r": r, "cov_update": args.cov,
                        "l2": f"working set {S} x 38 MB Sigma = {S * 38} MB per step " + ("> 126 MB L2 (inputs larger than L2)" if S * 38 > 126 else "<= L2: see single_session note"),
                        "steady_state_all_matched": bool(steady)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -94,6 +94,12 @@ typedef struct rekf_options {
   int map_loader;                /* REKF_MAP_LOADER_* */
   void *stream;                  /* optional cudaStream_t to run on (NULL: the handle creates one) */
   int use_graphs;                /* 1: replay steps through CUDA graphs where possible */
+  int pipeline_groups;           /* batch handles only: split the S sessions into this many groups, each advancing on
+                                    its own stream, so that one group's latency-bound kernels (association, Cholesky)
+                                    overlap another group's bandwidth-bound ones (TRSM, covariance SYRK).  Sessions
+                                    never interact, so results are bit-identical to 1.  0 or 1: one group. */
+  int syrk_reserve_sms;          /* with pipeline_groups > 1: SMs the persistent covariance SYRK leaves free for the
+                                    other groups' kernels (0: default) */
 } rekf_options;
 
 /* Fill with the reference defaults (launch/slam.launch:21-23 sigmas squared, DIFF model). */
@@ -147,6 +153,13 @@ REKF_API int rekf_get_mu(rekf_handle *h, int session, double *mu, int cap, int *
 REKF_API int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]);
 /* poses of all sessions in one read: S x 3 doubles (the per-step result of a batched replay) */
 REKF_API int rekf_batch_get_pose(rekf_handle *h, double *poses);
+/* Streaming form of the per-step result read for batch replay: request_poses enqueues, behind the work already
+ * issued, a device-to-host copy of every session's pose into a pinned ring owned by the handle and returns a ticket
+ * without waiting; fetch_poses waits for that ticket only and copies the S x 3 doubles out.  At most 64 tickets may
+ * be outstanding.  (The node's GetState() right after each message — ros_node.cc:478,515,592,638 — is
+ * rekf_get_pose / rekf_batch_get_pose; this pair is for consumers that can lag a few messages behind.) */
+REKF_API int rekf_batch_request_poses(rekf_handle *h, int64_t *ticket_out);
+REKF_API int rekf_batch_fetch_poses(rekf_handle *h, int64_t ticket, double *poses);
 /* landmark means + diagonal 2x2 blocks (what ros_node.cc:97-136,739-765 reads); cov row-major
  * (0,0),(0,1),(1,0),(1,1) per landmark like the save format. */
 REKF_API int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, int cap,

@@ -44,6 +44,8 @@ class RekfOptions(C.Structure):
         ("map_loader", C.c_int),
         ("stream", C.c_void_p),
         ("use_graphs", C.c_int),
+        ("pipeline_groups", C.c_int),
+        ("syrk_reserve_sms", C.c_int),
     ]
 
 
@@ -64,6 +66,8 @@ def make_options(
     stream=None,
     use_graphs=0,
     use_imu=False,
+    pipeline_groups=0,
+    syrk_reserve_sms=0,
 ):
     """Options with the reference's launch-file defaults (launch/slam.launch:21-23: sigma_v 0.05,
     sigma_w 0.08, sigma_z 0.05; squared the way ros_node.cc:207-237 squares them)."""
@@ -84,4 +88,6 @@ def make_options(
     o.map_loader = int(map_loader)
     o.stream = stream
     o.use_graphs = int(use_graphs)
+    o.pipeline_groups = int(pipeline_groups)
+    o.syrk_reserve_sms = int(syrk_reserve_sms)
     return o

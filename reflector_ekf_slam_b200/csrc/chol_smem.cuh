@@ -70,7 +70,7 @@ __device__ inline void invert_diag_block(const double *P, int jb, double *Dg, in
 
 __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L) {
   extern __shared__ double sm_d[];
-  const int s = blockIdx.x;
+  const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;

@@ -66,7 +66,8 @@ struct InputRef {
 };
 
 struct Layout {
-  int S;          // sessions
+  int S;          // sessions of the handle (extent of every [S]-leading array and of the TMA maps)
+  int s0, Sg;     // the sessions this launch covers: s0 .. s0+Sg-1 (a pipeline group; the whole batch when Sg == S)
   int Ncap;       // landmark capacity
   int ncap;       // 4 + 2*Ncap
   int ld;         // Σ / μ pitch, multiple of 128
@@ -102,7 +103,8 @@ struct Layout {
   double *Wdiag;  // [S][ld] exact fp64 diagonal of Wᵀ·W (tensor-core modes use it for Σ[i][i])
   unsigned char *Wflag;  // [S][ld] 1: this slot's row and column of the downdate are computed in fp64
   int *exact_list;       // [S][kMaxExactSlots] the flagged slots of this frame
-  int *step;      // device step counter for replay
+  int *step;      // device step counter for replay (one per pipeline group)
+  int *tile_counter;  // work-queue head of the persistent SYRK (one per pipeline group; reset by k_syrk_f64)
 };
 
 __host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }

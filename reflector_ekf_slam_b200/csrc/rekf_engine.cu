@@ -34,6 +34,35 @@ const char *kKernelNames[K_COUNT] = {"k_odometry", "k_observation_front", "k_inn
 
 struct ProfRecord { int id; cudaEvent_t a, b; };
 
+// A pipeline group: a contiguous range of the handle's sessions that advances on its own stream through its own
+// launches (Layout::s0 / Sg select the range).  Groups never exchange data; running several of them lets one
+// group's latency-bound kernels (association, innovation, Cholesky: a few CTAs) execute while another group's
+// bandwidth-bound ones (TRSM, covariance SYRK) own the rest of the GPU.  `whole` (all sessions, the handle's main
+// stream) is the only group when pipeline_groups <= 1 and the one used while per-kernel profiling is on.
+struct Group {
+  int s0 = 0, Sg = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  Layout L{};
+  // device mailbox for host-delivered messages of this group's sessions + pinned staging ring
+  char *mb_dev = nullptr;
+  char *mb_host = nullptr;
+  size_t mb_bytes = 0, off_odom = 0, off_time = 0, off_gps = 0, off_count = 0, off_xy = 0;
+  static constexpr int kSlots = 32;
+  cudaEvent_t slot_done[kSlots]{};
+  int slot = 0;
+  InputRef host_in{};
+  // replay graph (one step of this group)
+  cudaGraphExec_t step_graph = nullptr;
+  InputRef graph_in{};
+  int64_t step_launches = 0;   // kernel nodes in the captured step graph
+  cudaEvent_t done = nullptr;  // join marker
+  // asynchronous pose delivery: pinned ring written by stream-ordered copies
+  double *pose_host = nullptr;
+  static constexpr int kPoseSlots = 64;
+  cudaEvent_t pose_done[kPoseSlots]{};
+};
+
 }  // namespace
 
 struct rekf_handle {
@@ -44,15 +73,9 @@ struct rekf_handle {
   bool own_stream = false;
   std::string err;
   int64_t launches = 0;
-  int64_t step_launches = 0;   // kernel nodes in the captured step graph
-  // device mailbox for host-delivered messages + pinned staging ring
-  char *mb_dev = nullptr;
-  char *mb_host = nullptr;
-  size_t mb_bytes = 0, off_odom = 0, off_time = 0, off_gps = 0, off_count = 0, off_xy = 0;
-  static constexpr int kSlots = 32;
-  cudaEvent_t slot_done[kSlots]{};
-  int slot = 0;
-  InputRef host_in{};
+  Group whole;                 // every session, on `stream`
+  std::vector<Group> groups;   // pipeline groups (empty: `whole` is the only one)
+  int64_t pose_ticket = 0;     // asynchronous pose requests issued so far
   // staging for getters / setters
   double *stage_dev = nullptr;
   size_t stage_elems = 0;
@@ -66,9 +89,6 @@ struct rekf_handle {
   std::vector<cudaEvent_t> event_pool;
   double prof_us[K_COUNT]{};
   int prof_calls[K_COUNT]{};
-  // replay graph
-  cudaGraphExec_t step_graph = nullptr;
-  InputRef graph_in{};
   // tcgen05 SYRK resources
   bool chol_resident = false, solve_w2 = false;
   SyrkTc tc{};
@@ -128,22 +148,40 @@ cudaEvent_t take_event(rekf_handle *h) {
 struct ProfScope {
   rekf_handle *h;
   int id;
+  cudaStream_t stream;
   cudaEvent_t a = nullptr;
-  ProfScope(rekf_handle *h_, int id_) : h(h_), id(id_) {
+  ProfScope(rekf_handle *h_, int id_, cudaStream_t st) : h(h_), id(id_), stream(st) {
     ++h->launches;
     if (h->profiling) {
       a = take_event(h);
-      cudaEventRecord(a, h->stream);
+      cudaEventRecord(a, stream);
     }
   }
   ~ProfScope() {
     if (a) {
       cudaEvent_t b = take_event(h);
-      cudaEventRecord(b, h->stream);
+      cudaEventRecord(b, stream);
       h->prof.push_back({id, a, b});
     }
   }
 };
+
+// the groups that carry the hot path right now: per-kernel profiling wants one kernel on the GPU at a time
+inline std::vector<Group *> active_groups(rekf_handle *h) {
+  std::vector<Group *> v;
+  if (h->groups.empty() || h->profiling) v.push_back(&h->whole);
+  else for (auto &g : h->groups) v.push_back(&g);
+  return v;
+}
+
+// host-blocking join of every stream of the handle (cold paths: getters, setters, mode switches)
+inline cudaError_t join_all(rekf_handle *h) {
+  for (auto &g : h->groups) {
+    cudaError_t e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaStreamSynchronize(h->stream);
+}
 
 void drain_profile(rekf_handle *h) {
   for (auto &rec : h->prof) {
@@ -162,53 +200,57 @@ size_t smem_front(const Layout &L) { return sizeof(int) * 2 * (size_t)L.mcap + s
 size_t smem_chol(const Layout &L) { return sizeof(double) * ((size_t)(L.rcap + 1) * kPS + (size_t)kCholNb * kPS); }
 size_t smem_solve(const Layout &L) { return sizeof(double) * (size_t)L.rld * kYS; }
 
-int launch_odometry(rekf_handle *h, const InputRef &in) {
-  ProfScope p(h, K_ODOM);
-  k_odometry<<<h->L.S, 1024, 0, h->stream>>>(h->L, in);
+int launch_odometry(rekf_handle *h, Group &grp, const InputRef &in) {
+  ProfScope p(h, K_ODOM, grp.stream);
+  k_odometry<<<grp.Sg, 1024, 0, grp.stream>>>(grp.L, in);
   CK(cudaGetLastError());
   return 0;
 }
 
 // HandleObservationMessage as a fixed launch chain; sizes are read on the device.
-int launch_observation(rekf_handle *h, const InputRef &in) {
-  const Layout &L = h->L;
+int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
+  const Layout &L = grp.L;
+  cudaStream_t stream = grp.stream;
   {
-    ProfScope p(h, K_FRONT);
-    k_observation_front<<<L.S, 1024, smem_front(L), h->stream>>>(L, in);
+    ProfScope p(h, K_FRONT, stream);
+    k_observation_front<<<L.Sg, 1024, smem_front(L), stream>>>(L, in);
   }
   {
-    ProfScope p(h, K_INNOV);
+    ProfScope p(h, K_INNOV, stream);
     const int g = (L.rcap + 15) / 16;
-    k_innovation<<<dim3(g, g, L.S), dim3(16, 16), 0, h->stream>>>(L);
+    k_innovation<<<dim3(g, g, L.Sg), dim3(16, 16), 0, stream>>>(L);
   }
   {
-    ProfScope p(h, K_CHOL);
-    if (h->chol_resident) k_cholesky_smem<<<L.S, kCholSmemThreads, smem_chol_resident(L.rcap), h->stream>>>(L);
-    else k_cholesky<<<L.S, 1024, smem_chol(L), h->stream>>>(L);
+    ProfScope p(h, K_CHOL, stream);
+    if (h->chol_resident) k_cholesky_smem<<<L.Sg, kCholSmemThreads, smem_chol_resident(L.rcap), stream>>>(L);
+    else k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
   }
   {
-    ProfScope p(h, K_SOLVE);
-    if (h->solve_w2) k_solve_w3<<<dim3(L.ld / kW3Cols, 1, L.S), 256, smem_solve_w3(L.rld), h->stream>>>(L);
-    else k_solve_w<<<dim3(L.ld / kWCols, 1, L.S), 256, smem_solve(L), h->stream>>>(L);
+    ProfScope p(h, K_SOLVE, stream);
+    if (h->solve_w2) k_solve_w3<<<dim3(L.ld / kW3Cols, 1, L.Sg), 256, smem_solve_w3(L.rld), stream>>>(L);
+    else k_solve_w<<<dim3(L.ld / kWCols, 1, L.Sg), 256, smem_solve(L), stream>>>(L);
   }
   {
-    ProfScope p(h, K_SYRK);
+    ProfScope p(h, K_SYRK, stream);
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
-      k_syrk_f64<<<dim3(592, 1, L.S), 256, 0, h->stream>>>(L);
+      k_syrk_f64<<<dim3(592, 1, L.Sg), 256, 0, stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
       // fp64 side of the hybrid: the whole frame if st.exact_update, else the rows/columns of flagged slots, else nothing
-      k_syrk_f64<<<dim3(148, 1, L.S), 256, 0, h->stream>>>(L);
+      // (it also rewinds the tile queue of the persistent kernel that follows)
+      k_syrk_f64<<<dim3(148, 1, L.Sg), 256, 0, stream>>>(L);
       ++h->launches;                                              // two kernels inside this scope
-      int rc = h->persistent_syrk ? syrk_i8p_launch(h->tc8p, L, h->stream) : syrk_i8_launch(h->tc8, L, h->stream);
+      SyrkI8P tc8p = h->tc8p;
+      if (&grp == &h->whole) tc8p.reserve_sms = 0;                // nothing else is running beside the whole batch
+      int rc = h->persistent_syrk ? syrk_i8p_launch(tc8p, L, stream) : syrk_i8_launch(h->tc8, L, stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
-      int rc = syrk_tc_launch(h->tc, L, h->stream);
+      int rc = syrk_tc_launch(h->tc, L, stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
   }
   {
-    ProfScope p(h, K_AUGMENT);
-    k_augment<<<dim3((L.ncap + 255) / 256, 1, L.S), 256, 0, h->stream>>>(L, in);
+    ProfScope p(h, K_AUGMENT, stream);
+    k_augment<<<dim3((L.ncap + 255) / 256, 1, L.Sg), 256, 0, stream>>>(L, in);
   }
   CK(cudaGetLastError());
   return 0;
@@ -227,16 +269,72 @@ int stage_reserve(rekf_handle *h, size_t elems) {
 
 int read_state(rekf_handle *h, int s, SessionState *out) {
   if (s < 0 || s >= h->L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", s);
+  CK(join_all(h));
   CK(cudaMemcpyAsync(out, h->L.st + s, sizeof(SessionState), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;
 }
 
 // acquire the next pinned staging slot (waits only if the copy issued kSlots messages ago is pending)
-char *next_slot(rekf_handle *h) {
-  h->slot = (h->slot + 1) % rekf_handle::kSlots;
-  cudaEventSynchronize(h->slot_done[h->slot]);
-  return h->mb_host + (size_t)h->slot * h->mb_bytes;
+char *next_slot(Group &g) {
+  g.slot = (g.slot + 1) % Group::kSlots;
+  cudaEventSynchronize(g.slot_done[g.slot]);
+  return g.mb_host + (size_t)g.slot * g.mb_bytes;
+}
+
+// mailbox, staging ring, events and the Layout view of one group (sessions s0 .. s0+Sg-1, counters at `index`)
+int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t stream, bool own_stream) {
+  g.s0 = s0;
+  g.Sg = Sg;
+  g.stream = stream;
+  g.own_stream = own_stream;
+  g.L = h->L;
+  g.L.s0 = s0;
+  g.L.Sg = Sg;
+  g.L.step = h->L.step + index;
+  g.L.tile_counter = h->L.tile_counter + index;
+  const size_t S = (size_t)Sg;
+  const Layout &L = h->L;
+  g.off_odom = 0;
+  g.off_time = g.off_odom + S * 4 * sizeof(double);
+  g.off_gps = g.off_time + S * sizeof(double);
+  g.off_count = g.off_gps + S * 4 * sizeof(double);
+  g.off_xy = g.off_count + round_up((int)(S * sizeof(int)), 16);
+  g.mb_bytes = round_up((int)(g.off_xy + S * L.mcap * 2 * sizeof(float)), 256);
+  int rc = 0;
+  if ((rc = dev_alloc(h, &g.mb_dev, g.mb_bytes))) return rc;
+  CK(cudaMallocHost(&g.mb_host, g.mb_bytes * Group::kSlots));
+  std::memset(g.mb_host, 0, g.mb_bytes * Group::kSlots);
+  for (int i = 0; i < Group::kSlots; ++i) CK(cudaEventCreateWithFlags(&g.slot_done[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  CK(cudaMallocHost(&g.pose_host, sizeof(double) * 3 * S * Group::kPoseSlots));
+  for (int i = 0; i < Group::kPoseSlots; ++i) CK(cudaEventCreateWithFlags(&g.pose_done[i], cudaEventDisableTiming));
+  // kernels index every input by the absolute session: bias the bases by -s0 strides
+  InputRef &in = g.host_in;
+  in.odom_ss = 4;
+  in.time_ss = 1;
+  in.xy_ss = (long long)L.mcap * 2;
+  in.odom = reinterpret_cast<const double *>(g.mb_dev + g.off_odom) - (long long)s0 * in.odom_ss;
+  in.obs_time = reinterpret_cast<const double *>(g.mb_dev + g.off_time) - (long long)s0 * in.time_ss;
+  in.gps = reinterpret_cast<const double *>(g.mb_dev + g.off_gps) - (long long)s0 * 4;
+  in.obs_count = reinterpret_cast<const int *>(g.mb_dev + g.off_count) - s0;
+  in.obs_xy = reinterpret_cast<const float *>(g.mb_dev + g.off_xy) - (long long)s0 * in.xy_ss;
+  in.m_stride = L.mcap;
+  in.m_fixed = 0;
+  in.step = nullptr;
+  in.pose_out = nullptr;
+  in.pose_ss = 0;
+  return 0;
+}
+
+void destroy_group(Group &g) {
+  if (g.step_graph) cudaGraphExecDestroy(g.step_graph);
+  if (g.mb_host) cudaFreeHost(g.mb_host);
+  if (g.pose_host) cudaFreeHost(g.pose_host);
+  for (auto &e : g.slot_done) if (e) cudaEventDestroy(e);
+  for (auto &e : g.pose_done) if (e) cudaEventDestroy(e);
+  if (g.done) cudaEventDestroy(g.done);
+  if (g.own_stream && g.stream) cudaStreamDestroy(g.stream);
 }
 
 // ---- landmark map text format ---------------------------------------------------------------
@@ -299,6 +397,9 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   }
   Layout &L = h->L;
   L.S = sessions;
+  L.s0 = 0;
+  L.Sg = sessions;
+  int G = opts->pipeline_groups > 1 ? std::min(opts->pipeline_groups, sessions) : 1;
   L.Ncap = opts->max_landmarks > 0 ? opts->max_landmarks : 1024;
   L.mcap = opts->max_observations > 0 ? opts->max_observations : 128;
   if (L.mcap > 512) return fail(h, REKF_ERR_BAD_ARGUMENT, "max_observations %d > 512", L.mcap);
@@ -347,7 +448,8 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown cov_update %d", opts->cov_update);
   }
   if (opts->cov_update != REKF_COV_SIMT_F64 && (rc = dev_alloc(h, &L.Wdiag, S * L.ld))) return rc;
-  if ((rc = dev_alloc(h, &L.step, 1))) return rc;
+  if ((rc = dev_alloc(h, &L.step, G + 1))) return rc;
+  if ((rc = dev_alloc(h, &L.tile_counter, G + 1))) return rc;
 
   // initial state: time, pose (:8-11)
   {
@@ -362,31 +464,17 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     CK(cudaMemcpyAsync(L.mu, mu0.data(), sizeof(double) * S * L.ld, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
   }
-  // mailbox
-  h->off_odom = 0;
-  h->off_time = h->off_odom + S * 4 * sizeof(double);
-  h->off_gps = h->off_time + S * sizeof(double);
-  h->off_count = h->off_gps + S * 4 * sizeof(double);
-  h->off_xy = h->off_count + round_up((int)(S * sizeof(int)), 16);
-  h->mb_bytes = round_up((int)(h->off_xy + S * L.mcap * 2 * sizeof(float)), 256);
-  if ((rc = dev_alloc(h, &h->mb_dev, h->mb_bytes))) return rc;
-  CK(cudaMallocHost(&h->mb_host, h->mb_bytes * rekf_handle::kSlots));
-  std::memset(h->mb_host, 0, h->mb_bytes * rekf_handle::kSlots);
-  for (int i = 0; i < rekf_handle::kSlots; ++i) CK(cudaEventCreateWithFlags(&h->slot_done[i], cudaEventDisableTiming));
-  InputRef &in = h->host_in;
-  in.odom = reinterpret_cast<const double *>(h->mb_dev + h->off_odom);
-  in.obs_time = reinterpret_cast<const double *>(h->mb_dev + h->off_time);
-  in.gps = reinterpret_cast<const double *>(h->mb_dev + h->off_gps);
-  in.obs_count = reinterpret_cast<const int *>(h->mb_dev + h->off_count);
-  in.obs_xy = reinterpret_cast<const float *>(h->mb_dev + h->off_xy);
-  in.odom_ss = 4;
-  in.time_ss = 1;
-  in.xy_ss = (long long)L.mcap * 2;
-  in.m_stride = L.mcap;
-  in.m_fixed = 0;
-  in.step = nullptr;
-  in.pose_out = nullptr;
-  in.pose_ss = 0;
+  // groups: mailboxes, staging rings, streams
+  if ((rc = init_group(h, h->whole, 0, sessions, 0, h->stream, false))) return rc;
+  if (G > 1) {
+    h->groups.resize(G);
+    for (int g = 0; g < G; ++g) {
+      const int lo = (int)((long long)sessions * g / G), hi = (int)((long long)sessions * (g + 1) / G);
+      cudaStream_t st = nullptr;
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      if ((rc = init_group(h, h->groups[g], lo, hi - lo, g + 1, st, true))) return rc;
+    }
+  }
   CK(cudaEventCreate(&h->t0));
   CK(cudaEventCreate(&h->t1));
   // opt in to large dynamic shared memory where needed
@@ -411,6 +499,9 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     const char *why = syrk_i8_init(h->tc8, L);
     if (!why) why = syrk_i8p_init(h->tc8p, L);
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK setup failed: %s", why);
+    // with several groups in flight the persistent kernel leaves a few SMs to the other groups' narrow kernels
+    h->tc8p.reserve_sms = G > 1 ? (opts->syrk_reserve_sms > 0 ? opts->syrk_reserve_sms : 2 * ((sessions + G - 1) / G) + 4) : 0;
+    if (const char *e = std::getenv("REKF_SYRK_RESERVE_SMS")) h->tc8p.reserve_sms = G > 1 ? std::atoi(e) : 0;
   }
   if (opts->map_path && opts->map_path[0]) rekf_load_map_txt(h, opts->map_path);   // :36
   CK(cudaStreamSynchronize(h->stream));
@@ -419,14 +510,13 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
 
 int rekf_destroy(rekf_handle *h) {
   if (!h) return REKF_OK;
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->stream) join_all(h);
   drain_profile(h);
-  if (h->step_graph) cudaGraphExecDestroy(h->step_graph);
+  for (auto &g : h->groups) destroy_group(g);
+  destroy_group(h->whole);
   syrk_tc_destroy(h->tc);
   for (void *p : h->allocations) cudaFree(p);
   if (h->stage_dev) cudaFree(h->stage_dev);
-  if (h->mb_host) cudaFreeHost(h->mb_host);
-  for (auto &e : h->slot_done) if (e) cudaEventDestroy(e);
   for (auto &e : h->event_pool) cudaEventDestroy(e);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
@@ -445,12 +535,17 @@ int rekf_batch_handle_odometry(rekf_handle *h, const double *odom) {
   if (!h || !odom) return REKF_ERR_BAD_ARGUMENT;
   CK(cudaSetDevice(h->device));
   if (h->opts.use_imu) return REKF_OK;   // :213-222: with use_imu the reference does nothing
-  char *slot = next_slot(h);
-  const size_t bytes = (size_t)h->L.S * 4 * sizeof(double);
-  std::memcpy(slot + h->off_odom, odom, bytes);
-  CK(cudaMemcpyAsync(h->mb_dev + h->off_odom, slot + h->off_odom, bytes, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaEventRecord(h->slot_done[h->slot], h->stream));
-  return launch_odometry(h, h->host_in);
+  for (Group *gp : active_groups(h)) {
+    Group &g = *gp;
+    char *slot = next_slot(g);
+    const size_t bytes = (size_t)g.Sg * 4 * sizeof(double);
+    std::memcpy(slot + g.off_odom, odom + (size_t)g.s0 * 4, bytes);
+    CK(cudaMemcpyAsync(g.mb_dev + g.off_odom, slot + g.off_odom, bytes, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaEventRecord(g.slot_done[g.slot], g.stream));
+    int rc = launch_odometry(h, g, g.host_in);
+    if (rc) return rc;
+  }
+  return REKF_OK;
 }
 
 int rekf_handle_odometry(rekf_handle *h, double time, double vx, double vy, double wz) {
@@ -464,28 +559,32 @@ static int observation_common(rekf_handle *h, const double *times, const float *
                               int m_stride, const double *gps /*S x 4 or null*/) {
   const Layout &L = h->L;
   CK(cudaSetDevice(h->device));
-  char *slot = next_slot(h);
-  std::memcpy(slot + h->off_time, times, sizeof(double) * L.S);
-  double *g = reinterpret_cast<double *>(slot + h->off_gps);
-  if (gps) std::memcpy(g, gps, sizeof(double) * 4 * L.S);
-  else std::memset(g, 0, sizeof(double) * 4 * L.S);
-  int *cnt = reinterpret_cast<int *>(slot + h->off_count);
-  float *dst = reinterpret_cast<float *>(slot + h->off_xy);
-  int max_m = 0;
   for (int s = 0; s < L.S; ++s) {
-    const int m = counts[s];
-    if (m < 0) return fail(h, REKF_ERR_BAD_ARGUMENT, "negative observation count");
-    if (m > L.mcap) return fail(h, REKF_ERR_CAPACITY, "frame of %d observations exceeds max_observations %d", m, L.mcap);
-    cnt[s] = m;
-    max_m = std::max(max_m, m);
-    if (m > 0) std::memcpy(dst + (size_t)s * L.mcap * 2, xy + (size_t)s * m_stride * 2, sizeof(float) * 2 * m);
+    if (counts[s] < 0) return fail(h, REKF_ERR_BAD_ARGUMENT, "negative observation count");
+    if (counts[s] > L.mcap) return fail(h, REKF_ERR_CAPACITY, "frame of %d observations exceeds max_observations %d", counts[s], L.mcap);
   }
-  // one copy: time | gps | count | xy (only as far as the last session's data reaches)
-  const size_t end = h->off_xy + ((size_t)(L.S - 1) * L.mcap + (size_t)std::max(counts[L.S - 1], 0)) * 2 * sizeof(float);
-  CK(cudaMemcpyAsync(h->mb_dev + h->off_time, slot + h->off_time, end - h->off_time, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaEventRecord(h->slot_done[h->slot], h->stream));
-  (void)max_m;
-  return launch_observation(h, h->host_in);
+  for (Group *gp : active_groups(h)) {
+    Group &grp = *gp;
+    char *slot = next_slot(grp);
+    std::memcpy(slot + grp.off_time, times + grp.s0, sizeof(double) * grp.Sg);
+    double *g = reinterpret_cast<double *>(slot + grp.off_gps);
+    if (gps) std::memcpy(g, gps + (size_t)grp.s0 * 4, sizeof(double) * 4 * grp.Sg);
+    else std::memset(g, 0, sizeof(double) * 4 * grp.Sg);
+    int *cnt = reinterpret_cast<int *>(slot + grp.off_count);
+    float *dst = reinterpret_cast<float *>(slot + grp.off_xy);
+    for (int q = 0; q < grp.Sg; ++q) {
+      const int m = counts[grp.s0 + q];
+      cnt[q] = m;
+      if (m > 0) std::memcpy(dst + (size_t)q * L.mcap * 2, xy + (size_t)(grp.s0 + q) * m_stride * 2, sizeof(float) * 2 * m);
+    }
+    // one copy: time | gps | count | xy (only as far as the last session's data reaches)
+    const size_t end = grp.off_xy + ((size_t)(grp.Sg - 1) * L.mcap + (size_t)counts[grp.s0 + grp.Sg - 1]) * 2 * sizeof(float);
+    CK(cudaMemcpyAsync(grp.mb_dev + grp.off_time, slot + grp.off_time, end - grp.off_time, cudaMemcpyHostToDevice, grp.stream));
+    CK(cudaEventRecord(grp.slot_done[grp.slot], grp.stream));
+    int rc = launch_observation(h, grp, grp.host_in);
+    if (rc) return rc;
+  }
+  return REKF_OK;
 }
 
 int rekf_batch_handle_observation(rekf_handle *h, const double *times, const float *xy, const int *counts, int m_stride) {
@@ -508,51 +607,62 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
   const Layout &L = h->L;
   if (m > L.mcap) return fail(h, REKF_ERR_CAPACITY, "m %d exceeds max_observations %d", m, L.mcap);
   CK(cudaSetDevice(h->device));
-  InputRef in{};
-  in.odom = static_cast<const double *>(d_odom);
-  in.obs_time = static_cast<const double *>(d_obs_time);
-  in.obs_xy = static_cast<const float *>(d_obs_xy);
-  in.obs_count = nullptr;
-  in.gps = nullptr;
-  in.odom_ss = (long long)T * 4;
-  in.time_ss = T;
-  in.xy_ss = (long long)T * m * 2;
-  in.m_stride = m;
-  in.m_fixed = m;
-  in.step = L.step;
-  in.pose_out = static_cast<double *>(d_pose_out);
-  in.pose_ss = (long long)T * 3;
-  CK(cudaMemsetAsync(L.step, 0, sizeof(int), h->stream));
   const bool graphs = h->opts.use_graphs && !h->profiling;
-  if (graphs) {
-    const bool same = h->step_graph && std::memcmp(&in, &h->graph_in, sizeof(InputRef)) == 0;
+  std::vector<Group *> act = active_groups(h);
+  std::vector<InputRef> ins(act.size());
+  for (size_t gi = 0; gi < act.size(); ++gi) {
+    Group &g = *act[gi];
+    InputRef &in = ins[gi];
+    in = InputRef{};
+    in.odom = static_cast<const double *>(d_odom);
+    in.obs_time = static_cast<const double *>(d_obs_time);
+    in.obs_xy = static_cast<const float *>(d_obs_xy);
+    in.obs_count = nullptr;
+    in.gps = nullptr;
+    in.odom_ss = (long long)T * 4;
+    in.time_ss = T;
+    in.xy_ss = (long long)T * m * 2;
+    in.m_stride = m;
+    in.m_fixed = m;
+    in.step = g.L.step;
+    in.pose_out = static_cast<double *>(d_pose_out);
+    in.pose_ss = (long long)T * 3;
+    CK(cudaMemsetAsync(g.L.step, 0, sizeof(int), g.stream));
+    if (!graphs) continue;
+    const bool same = g.step_graph && std::memcmp(&in, &g.graph_in, sizeof(InputRef)) == 0;
     if (!same) {
-      if (h->step_graph) { cudaGraphExecDestroy(h->step_graph); h->step_graph = nullptr; }
-      cudaGraph_t g = nullptr;
+      if (g.step_graph) { cudaGraphExecDestroy(g.step_graph); g.step_graph = nullptr; }
+      cudaGraph_t cg = nullptr;
       const int64_t before = h->launches;
-      CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-      int rc = launch_odometry(h, in);
-      if (!rc) rc = launch_observation(h, in);
-      if (!rc) { ProfScope p(h, K_ADVANCE); k_advance_step<<<1, 1, 0, h->stream>>>(L.step); }
-      cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
+      CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+      int rc = launch_odometry(h, g, in);
+      if (!rc) rc = launch_observation(h, g, in);
+      if (!rc) { ProfScope p(h, K_ADVANCE, g.stream); k_advance_step<<<1, 1, 0, g.stream>>>(g.L.step); }
+      cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
       if (rc) return rc;
       if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-      CK(cudaGraphInstantiate(&h->step_graph, g, 0));
-      cudaGraphDestroy(g);
-      h->graph_in = in;
-      h->step_launches = h->launches - before;   // kernel nodes per step
+      CK(cudaGraphInstantiate(&g.step_graph, cg, 0));
+      cudaGraphDestroy(cg);
+      g.graph_in = in;
+      g.step_launches = h->launches - before;    // kernel nodes per step
       h->launches = before;                      // the capture pass itself launched nothing
     }
-    for (int t = 0; t < T; ++t) CK(cudaGraphLaunch(h->step_graph, h->stream));
-    h->launches += (int64_t)T * h->step_launches;
-    return REKF_OK;
   }
+  // groups are issued round-robin; each one's stream orders its own steps, nothing orders groups against each other
   for (int t = 0; t < T; ++t) {
-    int rc = launch_odometry(h, in);
-    if (rc) return rc;
-    if ((rc = launch_observation(h, in))) return rc;
-    ProfScope p(h, K_ADVANCE);
-    k_advance_step<<<1, 1, 0, h->stream>>>(L.step);
+    for (size_t gi = 0; gi < act.size(); ++gi) {
+      Group &g = *act[gi];
+      if (graphs) {
+        CK(cudaGraphLaunch(g.step_graph, g.stream));
+        h->launches += g.step_launches;
+        continue;
+      }
+      int rc = launch_odometry(h, g, ins[gi]);
+      if (rc) return rc;
+      if ((rc = launch_observation(h, g, ins[gi]))) return rc;
+      ProfScope p(h, K_ADVANCE, g.stream);
+      k_advance_step<<<1, 1, 0, g.stream>>>(g.L.step);
+    }
   }
   CK(cudaGetLastError());
   return REKF_OK;
@@ -561,7 +671,7 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
 // ---- accessors --------------------------------------------------------------------------------
 int rekf_sync(rekf_handle *h) {
   if (!h) return REKF_ERR_BAD_ARGUMENT;
-  CK(cudaStreamSynchronize(h->stream));
+  CK(join_all(h));
   std::vector<SessionState> st(h->L.S);
   CK(cudaMemcpy(st.data(), h->L.st, sizeof(SessionState) * h->L.S, cudaMemcpyDeviceToHost));
   for (int s = 0; s < h->L.S; ++s) {
@@ -588,7 +698,7 @@ int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, si
   else if (n == "mu") { src = L.mu + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
   else if (n == "sigma") { src = L.sigma + (size_t)session * L.ld * L.ld; size = sizeof(double) * L.ld * L.ld; }
   else return fail(h, REKF_ERR_BAD_ARGUMENT, "unknown debug buffer %s", name);
-  CK(cudaStreamSynchronize(h->stream));
+  CK(join_all(h));
   CK(cudaMemcpy(out, src, std::min(bytes, size), cudaMemcpyDeviceToHost));
   return REKF_OK;
 }
@@ -638,6 +748,7 @@ int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) 
   if (!h || !pose) return REKF_ERR_BAD_ARGUMENT;
   if (session < 0 || session >= h->L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
   const Layout &L = h->L;
+  CK(join_all(h));
   CK(cudaMemcpyAsync(pose, L.mu + (size_t)session * L.ld, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
   if (cov33)   // the block is symmetric, so row- vs column-major is immaterial
     CK(cudaMemcpy2DAsync(cov33, sizeof(double) * 3, L.sigma + (size_t)session * L.ld * L.ld, sizeof(double) * L.ld,
@@ -649,9 +760,40 @@ int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) 
 int rekf_batch_get_pose(rekf_handle *h, double *poses) {
   if (!h || !poses) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
-  CK(cudaMemcpy2DAsync(poses, sizeof(double) * 3, L.mu, sizeof(double) * L.ld, sizeof(double) * 3, L.S,
-                       cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
+  // every group reads its own sessions on its own stream, then the host waits for all of them
+  std::vector<Group *> act = active_groups(h);
+  for (Group *g : act)
+    CK(cudaMemcpy2DAsync(poses + (size_t)g->s0 * 3, sizeof(double) * 3, L.mu + (size_t)g->s0 * L.ld, sizeof(double) * L.ld,
+                         sizeof(double) * 3, g->Sg, cudaMemcpyDeviceToHost, g->stream));
+  for (Group *g : act) CK(cudaStreamSynchronize(g->stream));
+  return REKF_OK;
+}
+
+// Streaming form of the per-step result read: every group copies its sessions' poses into a pinned ring behind its
+// own step (stream-ordered, no host wait); the ticket is redeemed later.  At most Group::kPoseSlots tickets may be
+// outstanding.
+int rekf_batch_request_poses(rekf_handle *h, int64_t *ticket_out) {
+  if (!h || !ticket_out) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  const int slot = (int)(h->pose_ticket % Group::kPoseSlots);
+  for (Group *g : active_groups(h)) {
+    CK(cudaMemcpy2DAsync(g->pose_host + (size_t)slot * g->Sg * 3, sizeof(double) * 3, L.mu + (size_t)g->s0 * L.ld,
+                         sizeof(double) * L.ld, sizeof(double) * 3, g->Sg, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaEventRecord(g->pose_done[slot], g->stream));
+  }
+  *ticket_out = h->pose_ticket++;
+  return REKF_OK;
+}
+
+int rekf_batch_fetch_poses(rekf_handle *h, int64_t ticket, double *poses) {
+  if (!h || !poses) return REKF_ERR_BAD_ARGUMENT;
+  if (ticket < 0 || ticket >= h->pose_ticket || ticket + Group::kPoseSlots <= h->pose_ticket)
+    return fail(h, REKF_ERR_BAD_ARGUMENT, "pose ticket %lld is not outstanding", (long long)ticket);
+  const int slot = (int)(ticket % Group::kPoseSlots);
+  for (Group *g : active_groups(h)) {
+    CK(cudaEventSynchronize(g->pose_done[slot]));
+    std::memcpy(poses + (size_t)g->s0 * 3, g->pose_host + (size_t)slot * g->Sg * 3, sizeof(double) * 3 * g->Sg);
+  }
   return REKF_OK;
 }
 
@@ -732,7 +874,7 @@ int rekf_set_state(rekf_handle *h, int session, double time, const double vt[3],
   if (N > L.Ncap) return fail(h, REKF_ERR_CAPACITY, "%d landmarks exceed max_landmarks %d", N, L.Ncap);
   int rc = stage_reserve(h, (size_t)n * n + n);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(h->stream));
+  CK(join_all(h));
   double *dmu = h->stage_dev, *dsig = h->stage_dev + n;
   CK(cudaMemcpyAsync(dmu, mu, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpy2DAsync(dsig, sizeof(double) * n, sigma, sizeof(double) * ld, sizeof(double) * n, n, cudaMemcpyHostToDevice, h->stream));
@@ -755,7 +897,7 @@ int rekf_set_map(rekf_handle *h, const float *xy, const double *cov2x2, int coun
   if (count > L.mapcap) return fail(h, REKF_ERR_CAPACITY, "%d beacons exceed max_map_landmarks %d", count, L.mapcap);
   h->map_xy.assign(xy, xy + 2 * (size_t)count);
   h->map_cov.assign(cov2x2, cov2x2 + 4 * (size_t)count);
-  CK(cudaStreamSynchronize(h->stream));
+  CK(join_all(h));
   if (count > 0) {
     CK(cudaMemcpy(L.map_xy, xy, sizeof(float) * 2 * count, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(L.map_cov, cov2x2, sizeof(double) * 4 * count, cudaMemcpyHostToDevice));
@@ -857,11 +999,16 @@ int rekf_save_map_txt(rekf_handle *h, int session, const char *filebase) {
 // ---- timing ---------------------------------------------------------------------------------------
 int rekf_timer_start(rekf_handle *h) {
   if (!h) return REKF_ERR_BAD_ARGUMENT;
+  CK(join_all(h));                                   // the GPU is idle: t0 is stamped now, before any group's work
   CK(cudaEventRecord(h->t0, h->stream));
   return REKF_OK;
 }
 int rekf_timer_stop(rekf_handle *h, float *ms) {
   if (!h || !ms) return REKF_ERR_BAD_ARGUMENT;
+  for (auto &g : h->groups) {                        // t1 is stamped after the last group has finished
+    CK(cudaEventRecord(g.done, g.stream));
+    CK(cudaStreamWaitEvent(h->stream, g.done, 0));
+  }
   CK(cudaEventRecord(h->t1, h->stream));
   CK(cudaEventSynchronize(h->t1));
   CK(cudaEventElapsedTime(ms, h->t0, h->t1));
@@ -869,7 +1016,7 @@ int rekf_timer_stop(rekf_handle *h, float *ms) {
 }
 int rekf_profile_enable(rekf_handle *h, int enable) {
   if (!h) return REKF_ERR_BAD_ARGUMENT;
-  CK(cudaStreamSynchronize(h->stream));
+  CK(join_all(h));
   drain_profile(h);
   h->profiling = enable != 0;
   if (enable) {
@@ -880,7 +1027,7 @@ int rekf_profile_enable(rekf_handle *h, int enable) {
 }
 int rekf_profile_read(rekf_handle *h, const char **names, double *mean_us, int *calls, int cap, int *count_out) {
   if (!h) return REKF_ERR_BAD_ARGUMENT;
-  CK(cudaStreamSynchronize(h->stream));
+  CK(join_all(h));
   drain_profile(h);
   int c = 0;
   for (int k = 0; k < K_COUNT && c < cap; ++k) {

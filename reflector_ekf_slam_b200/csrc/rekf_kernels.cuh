@@ -133,7 +133,7 @@ __device__ inline int current_step(const InputRef &in) { return in.step ? *in.st
 
 // HandleOdometryMessage (:208-223): stale drop, latch vt_ BEFORE predicting, predict, set time.
 __global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in) {
-  const int s = blockIdx.x;
+  const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const double *msg = in.odom + (size_t)s * in.odom_ss + (size_t)current_step(in) * 4;
   const double time = msg[0];
@@ -162,7 +162,7 @@ constexpr int kMatchNew = 0, kMatchState = 1, kMatchMap = 2;
 
 __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in) {
   extern __shared__ int sm_i[];
-  const int s = blockIdx.x;
+  const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const int t_idx = current_step(in);
   const double time = in.obs_time[(size_t)s * in.time_ss + t_idx];
@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
 // S = H·Σ·Hᵀ + Q (lower triangle) and the ν row
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_innovation(Layout L) {
-  const int s = blockIdx.z;
+  const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
   const int q = blockIdx.x * 16 + threadIdx.x;   // row
@@ -363,7 +363,7 @@ constexpr int kPS = kCholNb + 1;   // padded panel pitch in shared memory
 
 __global__ void __launch_bounds__(1024, 1) k_cholesky(Layout L) {
   extern __shared__ double sm_d[];
-  const int s = blockIdx.x;
+  const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
@@ -508,7 +508,7 @@ __device__ inline float to_tf32(float x) {
 
 __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
   extern __shared__ double sm_d[];
-  const int s = blockIdx.z;
+  const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
@@ -628,15 +628,24 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
       for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
       const int e = (mx > 0.0 && c0 + cc < n) ? ilogb(mx) + 2 : 0;
       if (lane == 0) {
-        sexp[cc] = e; L.Wexp[(size_t)s * ld + c0 + cc] = e;
+        const int c = c0 + cc;
+        sexp[cc] = e; L.Wexp[(size_t)s * ld + c] = e;
+        L.Wscale[(size_t)s * ld + c] = scalbn(1.0, e);
         // The slices resolve 2^-29 of the row scale 2^e.  When the downdate removes almost all of a
         // state's variance (first update after dead reckoning, loop closure) that is no longer small
-        // against the posterior: such frames take the fp64 SYRK instead.
-        if (mx > 0.0 && c0 + cc < n) {
-          const int c = c0 + cc;
+        // against the posterior: such slots are flagged for k_syrk_exact_rows (same rule as k_solve_w3);
+        // more than kMaxExactSlots of them and the whole frame takes the fp64 SYRK.
+        bool exact = false;
+        if (mx > 0.0 && c < n) {
           const double post = Sg[(size_t)c * ld + c] - L.Wdiag[(size_t)s * ld + c];
-          if (!(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post) atomicOr(&L.st[s].exact_update, 1);
+          exact = !(post > 0.0) || scalbn(1.0, 2 * e) > kMaxSliceGain2 * post;
+          if (exact) {
+            const int pos = atomicAdd(&L.st[s].exact_slots, 1);
+            if (pos < kMaxExactSlots) L.exact_list[(size_t)s * kMaxExactSlots + pos] = c;
+            else atomicOr(&L.st[s].exact_update, 1);
+          }
         }
+        L.Wflag[(size_t)s * ld + c] = exact ? 1 : 0;
       }
     }
     __syncthreads();
@@ -678,8 +687,9 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
 // Σ −= Wᵀ·W on the fp64 pipe: 64x64 upper-triangular tiles, mirrored (exact symmetry by construction)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
-  const int s = blockIdx.z;
+  const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
+  if (L.tile_counter && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) *L.tile_counter = 0;   // queue head of the next launch
   const int r = st.r;
   if (r == 0) return;
   if (L.Wq && !st.exact_update) {           // the int8 tensor-core SYRK handles this frame, except flagged slots
@@ -740,7 +750,7 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
 // augmentation (:311-364) + end-of-step bookkeeping
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
-  const int s = blockIdx.z;
+  const int s = L.s0 + blockIdx.z;
   SessionState &st = L.st[s];
   const int t_idx = current_step(in);
   const int N = st.N;

@@ -33,7 +33,7 @@ __device__ __forceinline__ int swz(int row) { return ((row & 3) << 2) | ((row >>
 
 __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   extern __shared__ double sm_d[];
-  const int s = blockIdx.z;
+  const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;

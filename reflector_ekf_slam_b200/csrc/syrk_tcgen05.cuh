@@ -103,7 +103,7 @@ constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3
 __global__ void __launch_bounds__(kTcThreads, 1)
 k_syrk_tcgen05(Layout L, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
   extern __shared__ uint8_t smem_raw[];
-  const int s = blockIdx.y;
+  const int s = L.s0 + blockIdx.y;
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
@@ -282,7 +282,7 @@ inline const char *syrk_tc_init(SyrkTc &tc, const Layout &L) {
 inline int syrk_tc_launch(const SyrkTc &tc, const Layout &L, cudaStream_t stream) {
   if (!tc.ready) return -1;
   const int Tn = L.ld / 128;
-  k_syrk_tcgen05<<<dim3(Tn * (Tn + 1) / 2, L.S), kTcThreads, kTcSmemBytes, stream>>>(L, tc.map_hi, tc.map_lo);
+  k_syrk_tcgen05<<<dim3(Tn * (Tn + 1) / 2, L.Sg), kTcThreads, kTcSmemBytes, stream>>>(L, tc.map_hi, tc.map_lo);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -77,7 +77,7 @@ constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)k
 __global__ void __launch_bounds__(kTcThreads, 2)
 k_syrk_tcgen05_i8(Layout L, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b) {
   extern __shared__ uint8_t smem_raw[];
-  const int s = blockIdx.y;
+  const int s = L.s0 + blockIdx.y;
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0 || st.exact_update) return;                // deep-cancellation frames go to k_syrk_f64
@@ -297,7 +297,7 @@ inline const char *syrk_i8_init(SyrkI8 &tc, const Layout &L) {
 inline int syrk_i8_launch(const SyrkI8 &tc, const Layout &L, cudaStream_t stream) {
   if (!tc.ready) return -1;
   const int Tn = L.ld / 128;
-  k_syrk_tcgen05_i8<<<dim3(Tn * (Tn + 1), L.S), kTcThreads, kI8SmemBytes, stream>>>(L, tc.map_a, tc.map_b);
+  k_syrk_tcgen05_i8<<<dim3(Tn * (Tn + 1), L.Sg), kTcThreads, kI8SmemBytes, stream>>>(L, tc.map_a, tc.map_b);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 

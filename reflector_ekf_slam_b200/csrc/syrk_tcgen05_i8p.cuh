@@ -2,7 +2,10 @@
 // (Σ −= Wᵀ·W, reflector_ekf_slam.cc:308; arithmetic identical to syrk_tcgen05_i8.cuh — see there for the
 // digit-slice scheme).  What changes is the data movement, because the kernel is HBM-bound:
 //
-//   * one CTA per SM loops over (session, tile) work items: 128x64 tiles on/above the diagonal;
+//   * one CTA per SM pulls (session, tile) work items — 128x64 tiles on/above the diagonal — from a device-wide
+//     atomic queue (the operand producer fetches one item ahead and publishes it to the other roles through a
+//     4-entry shared-memory ring), so a CTA that starts late — its SM was still running another pipeline group's
+//     Cholesky — simply takes fewer tiles instead of stretching the launch;
 //   * Σ tiles travel by TMA in both directions: 128-row x 32-column half-tiles (2 boxes of 16 columns, 128-byte
 //     swizzle) in a four-slot shared-memory ring (two whole tiles) — full-line HBM reads issued a whole tile ahead, full-line
 //     writes, no partial sectors, no L1 thrash; only the mirrored lower-triangle copy is written from registers
@@ -22,12 +25,14 @@ constexpr int kPThreads = 384;                           // 12 warps: 8 epilogue
 constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ: 128 rows x 32 columns fp64 = 32 KB
 constexpr int kPSigSlots = 4;                            // Σ half-tile ring: two whole tiles, so loads run a full tile ahead
 constexpr int kPMaxSess = 64;                           // sessions whose (r, n) are cached in shared memory
+constexpr int kPQ = 4;                                   // work-item ring entries
 // operand ring + Σ ring + alignment slack + barriers + [2][64] column scales + [2][64] column flags + session table
-constexpr int kPSmemBytes = kI8Stages * kI8StageBytes + kPSigSlots * kPSigHalf + 1024 + 256 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8;
+constexpr int kPSmemBytes = kI8Stages * kI8StageBytes + kPSigSlots * kPSigHalf + 1024 + 256 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8 + 64;
 
 struct SyrkI8P {
   CUtensorMap map_a, map_b, map_sig;
   int num_sms = 148;
+  int reserve_sms = 0;          // SMs left to the other pipeline groups' latency-bound kernels
   bool ready = false;
 };
 
@@ -70,12 +75,14 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
            *sig_empty = bars + 12, *sig_done = bars + 16;
   uint64_t *sc_full = bars + 20;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 22);
+  uint64_t *q_full = bars + 23, *q_empty = bars + 27;                                      // work-item ring
   double *sc_tab = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [2][64] Wscale of the tile's columns
   unsigned char *fl_tab = reinterpret_cast<unsigned char *>(sc_tab + 2 * 64);             // [2][64] Wflag of the tile's columns
   int *sess_r = reinterpret_cast<int *>(fl_tab + 2 * 64);                                  // [kPMaxSess] r, 0 = nothing to do
   int *sess_n = sess_r + kPMaxSess;                                                        // [kPMaxSess] internal dimension
-  for (int q = threadIdx.x; q < min(L.S, kPMaxSess); q += kPThreads) {
-    const SessionState &st = L.st[q];
+  volatile int *q_item = sess_n + kPMaxSess;                                               // [kPQ] item index, -1 = no more work
+  for (int q = threadIdx.x; q < min(L.Sg, kPMaxSess); q += kPThreads) {
+    const SessionState &st = L.st[L.s0 + q];
     sess_r[q] = (st.r > 0 && !st.exact_update) ? st.r : 0;
     sess_n[q] = internal_dim(st.N);
   }
@@ -83,7 +90,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tn64 = L.ld / kI8TileN;
   const int tiles = (L.ld / 128) * (L.ld / 128 + 1);
-  const int total = tiles * L.S;
+  const int total = tiles * L.Sg;
 
   if (warp == 8) {
     if (lane == 0) {
@@ -94,6 +101,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       for (int i = 0; i < kPSigSlots; ++i) {
         mbar_init(&sig_full[i], 1); mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], 256);
       }
+      for (int i = 0; i < kPQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 11); }   // 11 consumer warps
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -106,30 +114,48 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   const uint32_t tmem = *tmem_slot;
   bool timeout = false;
 
-  // every role walks the same item sequence and applies the same skip rule
+  // item → (session, tile); false = nothing to do for it (the fetcher skips those, the other roles never see them)
   auto decode = [&](int item, int &s, int &i0, int &j0, int &r, int &n, bool &inA) -> bool {
-    s = item / tiles;
-    int rem = item - s * tiles, ti = 0;
+    const int sl = item / tiles;
+    s = L.s0 + sl;
+    int rem = item - sl * tiles, ti = 0;
     while (rem >= Tn64 - 2 * ti) { rem -= Tn64 - 2 * ti; ++ti; }
     const int tj = 2 * ti + rem;
     i0 = ti * 128; j0 = tj * kI8TileN;
     inA = rem < 2;
-    if (s < kPMaxSess) {
-      r = sess_r[s]; n = sess_n[s];
+    if (sl < kPMaxSess) {
+      r = sess_r[sl]; n = sess_n[sl];
     } else {
       const SessionState &st = L.st[s];
       r = (st.r > 0 && !st.exact_update) ? st.r : 0; n = internal_dim(st.N);
     }
     return r > 0 && j0 < n;
   };
+  // consumer side of the work-item ring: entry q of the sequence, -1 = the queue is drained
+  auto next_item = [&](uint32_t q, bool whole_warp) -> int {
+    const int slot = q & (kPQ - 1);
+    if (!mbar_wait_backoff(&q_full[slot], (q / kPQ) & 1)) { timeout = true; return -1; }
+    const int item = q_item[slot];
+    if (whole_warp) __syncwarp();
+    if (!whole_warp || lane == 0) mbar_arrive(&q_empty[slot]);
+    return item;
+  };
 
   if (warp == 8) {
     // ===== operand TMA producer =====
     if (lane == 0) {
       uint32_t kbc = 0;
-      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+      int nxt = atomicAdd(L.tile_counter, 1);              // fetched one item ahead: the round trip hides behind the loads
+      for (uint32_t q = 0; !timeout; ++q) {
         int s, i0, j0, r, n; bool inA;
-        if (!decode(item, s, i0, j0, r, n, inA)) continue;
+        int item = nxt;
+        while (item < total && !decode(item, s, i0, j0, r, n, inA)) item = atomicAdd(L.tile_counter, 1);
+        const int slot = q & (kPQ - 1);
+        if (!mbar_wait_backoff(&q_empty[slot], ((q / kPQ) & 1) ^ 1)) { timeout = true; break; }
+        q_item[slot] = item < total ? item : -1;
+        mbar_arrive(&q_full[slot]);
+        if (item >= total) break;
+        nxt = atomicAdd(L.tile_counter, 1);
         const int nkb = (r + kI8KBox - 1) / kI8KBox;
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
           const int stage = kbc & 1;
@@ -148,9 +174,11 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t kbc = 0, iter = 0;
-      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+      for (uint32_t q = 0; !timeout; ++q) {
+        const int item = next_item(q, false);
+        if (item < 0) break;
         int s, i0, j0, r, n; bool inA;
-        if (!decode(item, s, i0, j0, r, n, inA)) continue;
+        decode(item, s, i0, j0, r, n, inA);
         const int set = iter & 1;
         if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
         tc_fence_after();
@@ -187,9 +215,11 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     // ===== column scales / flags of every tile → shared memory (whole warp); Σ-tile TMA loads (lane 0, tiles strictly
     //       above the diagonal).  The scale slot is the accumulator set's: free once the epilogue released that set. =====
     uint32_t sit = 0, iter = 0;
-    for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+    for (uint32_t q = 0; !timeout; ++q) {
+      const int item = next_item(q, true);
+      if (item < 0) break;
       int s, i0, j0, r, n; bool inA;
-      if (!decode(item, s, i0, j0, r, n, inA)) continue;
+      decode(item, s, i0, j0, r, n, inA);
       const int set = iter & 1;
       if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
       {
@@ -221,9 +251,12 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     // ===== Σ-tile TMA store: waits until the 256 epilogue threads have rewritten a half-tile, stores it, frees it =====
     if (lane == 0) {
       uint32_t sit = 0;
-      for (int item = blockIdx.x; item < total && !timeout; item += gridDim.x) {
+      for (uint32_t q = 0; !timeout; ++q) {
+        const int item = next_item(q, false);
+        if (item < 0) break;
         int s, i0, j0, r, n; bool inA;
-        if (!decode(item, s, i0, j0, r, n, inA) || inA) continue;
+        decode(item, s, i0, j0, r, n, inA);
+        if (inA) continue;
         for (int h = 0; h < 2; ++h) {
           const int slot = ((sit & 1) << 1) | h;
           if (!mbar_wait_backoff(&sig_done[slot], (sit >> 1) & 1)) { timeout = true; break; }
@@ -247,9 +280,11 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     int row_s = -1, row_i0 = -1;                         // row scale / flag are reloaded only when the row block changes
     double si = 0.0;
     bool row_ok = false;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    for (uint32_t q = 0;; ++q) {
+      const int item = next_item(q, true);
+      if (item < 0) break;
       int s, i0, j0, r, n; bool inA;
-      if (!decode(item, s, i0, j0, r, n, inA)) continue;
+      decode(item, s, i0, j0, r, n, inA);
       const int set = iter & 1;
       const int i = i0 + il;
       double *Sg = L.sigma + (size_t)s * ld * ld;
@@ -369,7 +404,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       if (!inA) ++sit;
     }
   }
-  if (timeout) atomicOr(&L.st[0].flags, FLAG_TCGEN05_TIMEOUT);
+  if (timeout) atomicOr(&L.st[L.s0].flags, FLAG_TCGEN05_TIMEOUT);
   __syncthreads();
   if (warp == 8) {
     tc_fence_after();
@@ -413,8 +448,9 @@ inline const char *syrk_i8p_init(SyrkI8P &tc, const Layout &L) {
 
 inline int syrk_i8p_launch(const SyrkI8P &tc, const Layout &L, cudaStream_t stream) {
   if (!tc.ready) return -1;
-  const int total = (L.ld / 128) * (L.ld / 128 + 1) * L.S;
-  const int grid = total < tc.num_sms ? total : tc.num_sms;
+  const int total = (L.ld / 128) * (L.ld / 128 + 1) * L.Sg;
+  const int ctas = tc.num_sms - tc.reserve_sms > 1 ? tc.num_sms - tc.reserve_sms : 1;
+  const int grid = total < ctas ? total : ctas;
   k_syrk_tcgen05_i8p<<<grid, kPThreads, kPSmemBytes, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }

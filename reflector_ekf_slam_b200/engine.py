@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "rekf_get_mu", "rekf_get_pose", "rekf_batch_get_pose", "rekf_get_landmarks", "rekf_get_sigma", "rekf_get_match_result",
     "rekf_predict_state", "rekf_set_state", "rekf_set_map", "rekf_get_map", "rekf_load_map_txt", "rekf_save_map_txt",
     "rekf_sync", "rekf_stream", "rekf_timer_start", "rekf_timer_stop", "rekf_profile_enable", "rekf_profile_read",
-    "rekf_launch_count", "rekf_device_error_flags", "rekf_debug_copy",
+    "rekf_launch_count", "rekf_device_error_flags", "rekf_debug_copy", "rekf_batch_request_poses", "rekf_batch_fetch_poses",
 ]
 
 
@@ -85,6 +85,8 @@ def load_library(path=None):
         "rekf_launch_count": (C.c_int64, [vp]),
         "rekf_device_error_flags": (i, [vp, i, P(i)]),
         "rekf_debug_copy": (i, [vp, i, C.c_char_p, vp, C.c_size_t]),
+        "rekf_batch_request_poses": (i, [vp, P(C.c_int64)]),
+        "rekf_batch_fetch_poses": (i, [vp, C.c_int64, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -179,6 +181,18 @@ class EKFBatch:
         """(S, 3) poses of all sessions in one device→host read."""
         out = np.zeros((self.S, 3)) if out is None else out
         self._ck(self.lib.rekf_batch_get_pose(self.h, _ptr(out)))
+        return out
+
+    def request_poses(self):
+        """Enqueue a device→host copy of all poses behind the work issued so far; returns a ticket (no host wait)."""
+        t = C.c_int64()
+        self._ck(self.lib.rekf_batch_request_poses(self.h, C.byref(t)))
+        return t.value
+
+    def fetch_poses(self, ticket, out=None):
+        """Wait for `ticket` only and return its (S, 3) poses."""
+        out = np.zeros((self.S, 3)) if out is None else out
+        self._ck(self.lib.rekf_batch_fetch_poses(self.h, ticket, _ptr(out)))
         return out
 
     def landmarks(self, s=0):

@@ -85,6 +85,36 @@ def test_c3_warm_start_and_steps(engine_lib, cov):
     print(f"C3/{cov}: final |dmu| {d[0]:.2e} m, rel-Fro {d[1]:.2e}")
 
 
+@pytest.mark.parametrize("cov", ["f64", "i8"])
+def test_c4_omni_full_size(engine_lib, cov):
+    """Config C4 (N=4096, m=200, OMNI odometry, n=8195, r=400 — past the shared-memory-resident Cholesky): the
+    structured oracle builds the map in 21 frames, the snapshot is injected, 3 steady steps are compared
+    (association lists, means, the whole 8195x8195 covariance), plus exact symmetry of the result."""
+    from oracle.pyoracle import STRUCTURED, Oracle
+    from reflector_ekf_slam_b200.engine import ReflectorEKFSLAM
+    from reflector_ekf_slam_b200.synth import OMNI, make_stream
+    st = make_stream("C4", 3)
+    assert st["model"] == OMNI
+    orc = Oracle(algebra=STRUCTURED, odom_model=OMNI)
+    for k in range(st["n_build"]):
+        drive_oracle(orc, st, k)
+    t, mu, sig = orc.GetState()
+    assert mu.size == 3 + 2 * 4096
+    ekf = ReflectorEKFSLAM(odom_model=OMNI, max_landmarks=4096, max_observations=200, cov_update=COV_MODES[cov])
+    ekf.set_state(t, st["odom"][st["n_build"] - 1][1:4], mu, sig)
+    del sig
+    for k in range(st["n_build"], len(st["odom"])):
+        drive_engine(ekf, st, k)
+        drive_oracle(orc, st, k)
+        compare_matches(ekf, orc, f"C4 step {k}")
+        d = compare_state(ekf, orc, check_sigma=(k == len(st["odom"]) - 1), tag=f"C4/{cov} step {k}")
+    sp, _, nw = ekf.match_result()
+    assert len(sp) == 200 and len(nw) == 0 and ekf.error_flags() == 0
+    S = ekf.GetCoviarance()
+    assert np.array_equal(S, S.T)
+    print(f"C4/{cov}: final |dmu| {d[0]:.2e} m, rel-Fro {d[1]:.2e}")
+
+
 def test_covariance_stays_exactly_symmetric_and_psd(engine_lib):
     from reflector_ekf_slam_b200.synth import make_stream
     st = make_stream("T1", 20)
@@ -259,3 +289,48 @@ def test_replay_device_matches_host_path(engine_lib):
             assert np.array_equal(d_pose[s, -1].cpu().numpy(), ref.mu(s)[:3])
         outs.append(d_pose.cpu().numpy())
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("groups", [2, 3])
+def test_pipeline_groups_bitwise(engine_lib, groups):
+    """pipeline_groups > 1 (each group of sessions on its own stream, persistent SYRK fed from the atomic tile queue)
+    produces bit-identical states to the single-group batch, through the host path, the device replay (with and
+    without graphs) and the streaming pose read."""
+    import torch
+    from reflector_ekf_slam_b200.engine import EKFBatch
+    from reflector_ekf_slam_b200.synth import make_stream
+    S, T = 5, 8
+    sts = [make_stream("T1", 2 * T, session=s) for s in range(S)]
+    nb, m = sts[0]["n_build"], sts[0]["m"]
+    kw = dict(odom_model=sts[0]["model"], max_landmarks=60, max_observations=12)
+    ref = EKFBatch(S, **kw)
+    engines = [ref] + [EKFBatch(S, pipeline_groups=groups, use_graphs=g, **kw) for g in (0, 1)]
+    tickets = []
+    for k in range(nb + T):
+        for e in engines:
+            e.handle_odometry(np.stack([st["odom"][k] for st in sts]))
+            e.handle_observation(np.array([st["obs_time"][k] for st in sts]), np.stack([st["obs_xy"][k] for st in sts]),
+                                 np.array([st["obs_count"][k] for st in sts]))
+        tickets.append((engines[1].request_poses(), ref.poses().copy()))
+        if len(tickets) > 4:
+            t, want = tickets.pop(0)
+            assert np.array_equal(engines[1].fetch_poses(t), want)
+    for t, want in tickets:
+        assert np.array_equal(engines[1].fetch_poses(t), want)
+    dev = torch.device("cuda:0")
+    d_odom = torch.tensor(np.stack([st["odom"][nb + T:] for st in sts]), device=dev)
+    d_time = torch.tensor(np.stack([st["obs_time"][nb + T:] for st in sts]), device=dev)
+    d_xy = torch.tensor(np.stack([st["obs_xy"][nb + T:] for st in sts]), device=dev)
+    poses = []
+    for e in engines:
+        d_pose = torch.zeros(S, T, 3, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        e.replay_device(d_odom.data_ptr(), d_time.data_ptr(), d_xy.data_ptr(), T, m, d_pose.data_ptr())
+        e.sync()
+        poses.append(d_pose.cpu().numpy())
+    for e, p in zip(engines[1:], poses[1:]):
+        assert np.array_equal(p, poses[0])
+        for s in range(S):
+            assert np.array_equal(e.mu(s), ref.mu(s)) and np.array_equal(e.sigma(s), ref.sigma(s))
+            for a, b in zip(e.match_result(s), ref.match_result(s)):
+                assert np.array_equal(a, b)
