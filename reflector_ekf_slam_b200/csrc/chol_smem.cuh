@@ -4,17 +4,21 @@
 // inverted, and ν rides along as an extra row that comes out as L⁻¹ν (the mean update then is Wᵀ·L⁻¹ν).
 // This kernel is the serial spine of the step — r pivots, each a dependent rsqrt — so the design goal is
 // latency, not throughput:
-//   * right-looking, 32-column panels, everything in shared memory (packed block columns, ~215 KB at r=200),
-//     filled with cp.async so the global-memory latency is paid once;
-//   * phase A: the 32x32 diagonal block is factored by ONE warp with the block in registers (lane = row).
+//   * right-looking with look-ahead, 32-column panels, everything in shared memory: packed block columns, ~215 KB at
+//     r=200, COLUMN-major like the global buffer, so the triangle comes in and goes out as one cp.async.bulk per
+//     column (the L1 left beside 215 KB of shared memory is ~13 KB, and element-wise LDG/cp.async/STG through it ran
+//     at ~12 B/clk: 13k + 16k cycles for the two transfers; the bulk engine does them in ~3k + ~6k);
+//   * phase 1: the 32x32 diagonal block is factored by ONE warp with the block in registers (lane = row).
 //     Per column the next pivot is formed from registers and shuffled out before the column broadcast, so
 //     the rsqrt chain (the critical path) overlaps the rank-1 update; no CTA barrier inside the block.
-//     Meanwhile the other seven warps invert the PREVIOUS diagonal block (X = L_bb⁻¹, five interleaved
-//     substitution chains per warp) — the TRSM kernel consumes these inverses;
-//   * phase B: every row below the block (and the ν row) is owned by one thread, held in registers, and
+//     In its shadow warp 1 inverts the PREVIOUS diagonal block (X = L_bb⁻¹, lane = column of X held in registers,
+//     broadcast reads of L, no shuffles) — the TRSM kernel consumes these inverses — and warps 2-7 apply the previous
+//     panel's rank-32 update to everything right of the current block column;
+//   * phase 2: every row below the block (and the ν row) is owned by one thread, held in registers, and
 //     solved against the diagonal block by column-oriented substitution (31−j independent FMAs per step);
-//   * phase C: trailing rank-32 update on the fp64 tensor pipe (mma.sync m8n8k4 → DMMA; full rate on
-//     B200): a warp task is one 8-row tile against all column tiles left of it, A fragments in registers;
+//   * phase 3: the panel's update of the NEXT block column only (all warps) — the one thing the next factorisation
+//     waits for.  Updates run on the fp64 tensor pipe (mma.sync m8n8k4 → DMMA): a warp task is one 8-row tile
+//     against its column tiles, A fragments in registers;
 //   * L goes back to global memory once, at the end.
 // 256 threads (the per-thread 32-double rows stay in registers), one CTA per session.
 // Larger r (config C4) falls back to k_cholesky (global-memory panels).
@@ -25,13 +29,25 @@
 namespace rekf {
 
 constexpr int kCholSmemThreads = 256;
-constexpr int kPS2 = kCholNb + 4;    // pitch 36: DMMA fragment loads (8 rows x 4 k) are bank-conflict free
 
-// packed block-column storage: block column b holds rows 32b..R1-1 (R1 = r+1 incl. the ν row), pitch kPS2
-__host__ __device__ inline int chol_panel_off(int R1, int b) { return (b * R1 - 16 * b * (b - 1)) * kPS2; }
+// Packed COLUMN-major block columns — the same orientation as the global S / L buffer, so that the triangle moves in
+// and out as one bulk copy (cp.async.bulk) per column.  Block column b holds columns 32b..32b+31, rows 32b..R1-1
+// (R1 = r+1 incl. the ν row) at pitch lda(b) ≡ 8 (mod 16) doubles: the DMMA fragment loads (8 rows x 4 k) then hit
+// every bank pair exactly twice per 256-byte request (the minimum), and lane = row accesses are contiguous.
+// The last block column always has room for a full 32x32 diagonal block + the ν row (a partial last block is padded
+// with the identity in shared memory, so every block runs the same code).
+__host__ __device__ inline int chol_lda(int R1, int b) {
+  const int rows = R1 - 32 * b;
+  return ((max(rows, kCholNb + 1) + 7) & ~15) + 8;
+}
+__host__ __device__ inline int chol_col_off(int R1, int b) {
+  int off = 0;
+  for (int q = 0; q < b; ++q) off += kCholNb * chol_lda(R1, q);
+  return off;
+}
 inline size_t smem_chol_resident(int rcap) {
   const int R1 = rcap + 1, nb = (rcap + kCholNb - 1) / kCholNb;
-  return sizeof(double) * ((size_t)chol_panel_off(R1, nb) + 2 * 32 + 32);
+  return sizeof(double) * ((size_t)chol_col_off(R1, nb) + 2 * 32 + 2 * 32 + 2 + 8);
 }
 
 // D(8x8) = A(8x4)·B(4x8) + C on the fp64 tensor pipe.  Fragments (lane = 4·g + t): a = A[g][t], b = B[t][g],
@@ -41,36 +57,61 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
-// X = D⁻¹ for the jb x jb lower-triangular block at P (pitch kPS2), written to Dg[32][32] (identity past jb).
-// Called by `nw` warps (index wi); each interleaves its columns c = wi, wi+nw, ... as independent chains.
-__device__ inline void invert_diag_block(const double *P, int jb, double *Dg, int wi, int nw, int lane) {
-  constexpr int kMaxCols = 5;
-  const double dinv = (lane < jb) ? 1.0 / P[lane * kPS2 + lane] : 1.0;
-  double t[kMaxCols], x[kMaxCols];
-  int col[kMaxCols];
+// trailing update A[i][c] −= Σ_k P[i][k]·P[c][k] on the fp64 tensor pipe for the 8-column tiles ct_lo..ct_hi (counted
+// from column Jp+32) and every row tile at or below them; Pp = block column Jp/32 (rows Jp.., already solved).
+// The product is formed transposed — D[m][n] with m = column, n = row — so that a lane's accumulator pair is two
+// consecutive ROWS of one column: one 16-byte access in the column-major panels.  A warp task is one 8-row tile against
+// its column tiles, the row tile's fragments in registers; two accumulator chains per tile (k halves).
+__device__ __forceinline__ void chol_trailing(double *A, const int *tab, const double *Pp, int lda_p, int Jp, int R1, int r,
+                                              int ct_lo, int ct_hi, int wi, int nw, int lane) {
+  const int rows = R1 - Jp;
+  const int T = R1 - (Jp + kCholNb);                        // remaining rows (incl. ν)
+  const int Tc = r - (Jp + kCholNb);                        // remaining columns
+  if (T <= 0 || Tc <= 0) return;
+  const int nrt = (T + 7) / 8, nct = (Tc + 7) / 8;
+  const int ntask = nrt - ct_lo;                            // row tiles ct_lo .. nrt-1
+  if (ntask <= 0 || ct_lo >= nct) return;
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int q = 0; q * nw < ntask; ++q) {                    // snake order balances the triangular task sizes
+    const int idx = q * nw + ((q & 1) ? nw - 1 - wi : wi);
+    if (idx >= ntask) continue;
+    const int rt = nrt - 1 - idx;
+    const int irow = kCholNb + 8 * rt + g;                  // panel-relative row held by this lane's row-tile fragment
+    const double *rp = Pp + t4 * lda_p + min(irow, rows - 1);
+    double rf[8];
 #pragma unroll
-  for (int u = 0; u < kMaxCols; ++u) {
-    col[u] = wi + u * nw;
-    t[u] = (lane == col[u]) ? 1.0 : 0.0;
-    x[u] = 0.0;
-  }
-  for (int k = 0; k < kCholNb; ++k) {
-    const double lk = (lane > k && lane < jb && k < jb) ? P[min(lane, jb - 1) * kPS2 + k] : 0.0;
+    for (int ks = 0; ks < 8; ++ks) rf[ks] = -rp[4 * ks * lda_p];
+    const int gi = Jp + kCholNb + 8 * rt + 2 * t4;          // accumulator rows gi, gi+1 ...
+    const int ctmax = min(min(rt, nct - 1), ct_hi);
+    for (int ct = ct_lo; ct <= ctmax; ++ct) {
+      const int crow = kCholNb + 8 * ct + g;                // column tile: its columns are rows crow of the panel
+      const double *cf = Pp + t4 * lda_p + min(crow, rows - 1);
+      const int gc = Jp + crow;                             // ... of column gc
+      const bool ok = (gc < r) && (gi < R1);
+      const int cbk = min(gc >> 5, 7);
+      double *cp = A + tab[cbk] + (gc - cbk * kCholNb) * tab[8 + cbk] + (gi - cbk * kCholNb);
+      double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;        // two accumulator chains (k halves)
+      if (ok) { const double2 cv = *reinterpret_cast<const double2 *>(cp); c0 = cv.x; c1 = cv.y; }
 #pragma unroll
-    for (int u = 0; u < kMaxCols; ++u) {
-      const double xk = __shfl_sync(0xffffffffu, t[u] * dinv, k);
-      if (lane == k) x[u] = xk;
-      t[u] = fma(-lk, xk, t[u]);
+      for (int ks = 0; ks < 4; ++ks) {
+        dmma884(c0, c1, cf[4 * ks * lda_p], rf[ks], c0, c1);
+        dmma884(e0, e1, cf[4 * (ks + 4) * lda_p], rf[ks + 4], e0, e1);
+      }
+      c0 += e0; c1 += e1;
+      if (ok) {
+        if (gi + 1 < R1) *reinterpret_cast<double2 *>(cp) = make_double2(c0, c1);
+        else cp[0] = c0;
+      }
     }
   }
-#pragma unroll
-  for (int u = 0; u < kMaxCols; ++u)
-    if (col[u] < kCholNb) Dg[lane * kCholNb + col[u]] = x[u];
 }
 
 __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L) {
-  extern __shared__ double sm_d[];
-  const int s = L.s0 + blockIdx.x;
+  extern __shared__ __align__(128) double sm_d[];
+  // Launched as clusters of two CTAs of which only rank 0 works: a cluster pair is the two SMs of one TPC, and two
+  // factorisations sharing a TPC run their fp64-bound phases at half speed (measured: phase 2 25k → 40k cycles).
+  if (blockIdx.x & 1) return;
+  const int s = L.s0 + (blockIdx.x >> 1);
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
@@ -80,8 +121,11 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L)
   double *Sb = L.Sbuf + (size_t)s * L.rld * sld;
   double *Dinv = L.Dinv + (size_t)s * (L.rld / kCholNb) * kCholNb * kCholNb;
   double *A = sm_d;                                         // packed block columns
-  double *cb = sm_d + chol_panel_off(R1, nblk);             // [2][32] column broadcast buffer of the panel warp
-  double *invd = cb + 64;                                   // [32] reciprocals of the current diagonal
+  double *cb = sm_d + chol_col_off(R1, nblk);               // [2][32] column broadcast buffer of the panel warp
+  double *invd = cb + 64;                                   // [2][32] reciprocals of the diagonal, ping-pong by block parity
+  uint64_t *bar = reinterpret_cast<uint64_t *>(invd + 64);  // transaction barrier of the bulk load
+  int *tab = reinterpret_cast<int *>(bar + 2);              // [8] block-column offsets, [8] pitches
+  if (threadIdx.x < 8) { tab[threadIdx.x] = chol_col_off(R1, threadIdx.x); tab[8 + threadIdx.x] = chol_lda(R1, threadIdx.x); }
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT / 32;
   bool bad = false;
 #ifdef REKF_CHOL_TIMING
@@ -93,36 +137,66 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L)
 #endif
   REKF_TSTAMP();
 
-  // ---- load the lower triangle (+ ν row) with cp.async: warp per column, lanes over rows -------------------
-  for (int c = warp; c < r; c += NW) {
-    const int b = c >> 5, jj = c & 31, base = b << 5;
-    double *P = A + chol_panel_off(R1, b) + jj;
-    const double *src = Sb + (size_t)c * sld;
-    for (int i = base + lane; i < R1; i += 32)
-      if (i >= c)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(P + (i - base) * kPS2)), "l"(src + i) : "memory");
+  // ---- load the lower triangle (+ ν row): one bulk copy per column, rows 32b.. (the few entries above the diagonal
+  //      inside the diagonal block come along and are never read) -------------------------------------------------------
+  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    unsigned total = 0;
+    for (int b = 0; b < nblk; ++b) total += (unsigned)min(kCholNb, r - b * kCholNb) * (unsigned)((R1 - b * kCholNb + 1) & ~1) * 8u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(total) : "memory");
   }
-  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  // this thread's column (r <= 224 < 256 threads): shared-memory home, global home, bytes (a multiple of 16)
+  const int cb_b = tid >> 5;
+  double *col_s = A + chol_col_off(R1, min(cb_b, nblk - 1)) + (tid & 31) * chol_lda(R1, min(cb_b, nblk - 1));
+  double *col_g = Sb + (size_t)tid * sld + cb_b * kCholNb;
+  const unsigned col_bytes = (tid < r) ? (unsigned)((R1 - cb_b * kCholNb + 1) & ~1) * 8u : 0u;
+  if (col_bytes)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(col_s)), "l"(col_g), "r"(col_bytes), "r"(bar_a) : "memory");
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar_a), "r"(0) : "memory");
+  }
   REKF_TSTAMP();
 
+  const int jb_last = r - (nblk - 1) * kCholNb;             // true width of the last block
   for (int b = 0; b < nblk; ++b) {
-    const int J = b * kCholNb, jb = min(kCholNb, r - J), rows = R1 - J;
-    double *P = A + chol_panel_off(R1, b);
+    const int J = b * kCholNb;
+    const int lda = chol_lda(R1, b);
+    double *P = A + chol_col_off(R1, b);                    // element (J + i, J + c) at P[c * lda + i]
+    double *rinv = invd + (b & 1) * kCholNb;
+    if (b == nblk - 1 && jb_last < kCholNb) {
+      // partial last block → identity-padded full block: ν moves from relative row jb to row 32, rows/columns
+      // jb..31 become the identity (all trailing updates into this block column are done: see phase 3 / phase 1)
+      if (tid < kCholNb) {
+        const int c = tid;
+        double *col = P + c * lda;
+        const double nu_c = (c < jb_last) ? col[jb_last] : 0.0;
+        for (int i = (c < jb_last ? jb_last : 0); i < kCholNb; ++i) col[i] = (i == c) ? 1.0 : 0.0;
+        col[kCholNb] = nu_c;
+      }
+      __syncthreads();
+    }
+    const int rows = (b == nblk - 1) ? kCholNb + 1 : R1 - J;   // rows of this block column (the last one: block + ν)
 
+    // ---- phase 1: warp 0 factors the diagonal block; meanwhile warp 1 inverts the previous diagonal block (for the
+    //      TRSM kernel) and warps 2.. finish the previous panel's trailing update right of block column b ------------
     if (warp == 0) {
-      // ---- phase A: one warp factors the jb x jb diagonal block held in registers ----------------------
       double a[kCholNb];
 #pragma unroll
-      for (int jj = 0; jj < kCholNb; ++jj)
-        a[jj] = (lane < jb && jj < jb) ? ((jj <= lane) ? P[min(lane, jb - 1) * kPS2 + jj] : 0.0) : ((jj == lane) ? 1.0 : 0.0);
+      for (int jj = 0; jj < kCholNb; ++jj) a[jj] = (jj <= lane) ? P[jj * lda + lane] : 0.0;
       double d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int j = 0; j < kCholNb; ++j) {
-        if (j < jb && !(d > 0.0)) bad = true;
+        if (!(d > 0.0)) bad = true;
         const double inv = rsqrt(d);
         const double l = (lane == j) ? d * inv : a[j] * inv;
-        if (lane == j) invd[j] = inv;
+        if (lane == j) rinv[j] = inv;
         if (j + 1 < kCholNb) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);   // next pivot, early
         cb[(j & 1) * 32 + lane] = l;
         __syncwarp();
@@ -130,115 +204,71 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L)
         for (int jj = j + 1; jj < kCholNb; ++jj) a[jj] = fma(-l, cb[(j & 1) * 32 + jj], a[jj]);
         a[j] = l;
       }
-      if (lane < jb) {
 #pragma unroll
-        for (int jj = 0; jj < kCholNb; ++jj)
-          if (jj <= lane) P[lane * kPS2 + jj] = a[jj];
-      }
+      for (int jj = 0; jj < kCholNb; ++jj)
+        if (jj <= lane) P[jj * lda + lane] = a[jj];
     } else if (b > 0) {
-      // ---- meanwhile: inverse of the previous (full) diagonal block, for the TRSM kernel --------------------
-      invert_diag_block(A + chol_panel_off(R1, b - 1), kCholNb, Dinv + (size_t)(b - 1) * kCholNb * kCholNb, warp - 1, NW - 1, lane);
+      chol_trailing(A, tab, A + chol_col_off(R1, b - 1), chol_lda(R1, b - 1), J - kCholNb, R1, r, 4, 1 << 30, warp - 1, NW - 1, lane);
     }
     __syncthreads();
     REKF_TSTAMP();
 
-    // ---- phase B: rows below the block (incl. ν), one thread per row, substitution in registers ----------
-    if (jb == kCholNb) {
-      for (int ii = kCholNb + tid; ii < rows; ii += NT) {
-        double a[kCholNb];
-        double *row = P + ii * kPS2;
+    // ---- phase 2: rows below the block (incl. ν), one thread per row, substitution in registers; column j of the
+    //      diagonal block is contiguous: 16-byte broadcast reads.  32 more threads run the same substitution on the rows
+    //      of the identity: their results are the columns of X = L_bb⁻¹, the block inverse the TRSM kernel consumes -----
+    for (int ii = kCholNb + tid; ii < rows + kCholNb; ii += NT) {
+      const bool real = ii < rows;
+      const int c = ii - rows;                               // identity row (column of X) when !real
+      double a[kCholNb];
 #pragma unroll
-        for (int jj = 0; jj < kCholNb; jj += 2) {
-          const double2 t = *reinterpret_cast<const double2 *>(row + jj);
-          a[jj] = t.x; a[jj + 1] = t.y;
+      for (int jj = 0; jj < kCholNb; ++jj) a[jj] = real ? P[jj * lda + ii] : ((jj == c) ? 1.0 : 0.0);
+#pragma unroll
+      for (int j = 0; j < kCholNb; ++j) {
+        const double l = a[j] * rinv[j];
+        const double *lc = P + j * lda;                      // column j of the diagonal block
+#pragma unroll
+        for (int p = (j + 1) >> 1; p < kCholNb / 2; ++p) {
+          const double2 v = *reinterpret_cast<const double2 *>(lc + 2 * p);
+          if (2 * p > j) a[2 * p] = fma(-l, v.x, a[2 * p]);
+          a[2 * p + 1] = fma(-l, v.y, a[2 * p + 1]);
         }
-#pragma unroll
-        for (int j = 0; j < kCholNb; ++j) {
-          const double l = a[j] * invd[j];
-          const double *lj = P + j;                          // column j of the diagonal block: P[jj][j]
-#pragma unroll
-          for (int jj = j + 1; jj < kCholNb; ++jj) a[jj] = fma(-l, lj[jj * kPS2], a[jj]);
-          a[j] = l;
-        }
-#pragma unroll
-        for (int jj = 0; jj < kCholNb; jj += 2) *reinterpret_cast<double2 *>(row + jj) = make_double2(a[jj], a[jj + 1]);
+        a[j] = l;
       }
-    } else {                                                 // last, partial block: only the ν row is below it
-      for (int ii = jb + tid; ii < rows; ii += NT) {
-        double *row = P + ii * kPS2;
-        for (int j = 0; j < jb; ++j) {
-          const double l = row[j] * invd[j];
-          for (int jj = j + 1; jj < jb; ++jj) row[jj] = fma(-l, P[jj * kPS2 + j], row[jj]);
-          row[j] = l;
-        }
+      if (real) {
+#pragma unroll
+        for (int jj = 0; jj < kCholNb; ++jj) P[jj * lda + ii] = a[jj];
+      } else {
+        double *Dg = Dinv + (size_t)b * kCholNb * kCholNb;   // X[j][c], row-major
+#pragma unroll
+        for (int jj = 0; jj < kCholNb; ++jj) Dg[jj * kCholNb + c] = a[jj];
       }
     }
     __syncthreads();
     REKF_TSTAMP();
 
-    // ---- phase C: trailing update A[i][c] −= Σ_k P[i][k]·P[c][k], J+32 <= c <= i, on the fp64 tensor pipe ---------
-    const int T = R1 - (J + kCholNb);                       // remaining rows (incl. ν); <= 0 on the last block
-    const int Tc = r - (J + kCholNb);                       // remaining columns
-    if (T > 0 && Tc > 0) {
-      const int nrt = (T + 7) / 8, nct = (Tc + 7) / 8;
-      const int g = lane >> 2, t4 = lane & 3;
-      for (int q = 0;; ++q) {                               // snake order balances the triangular task sizes
-        const int idx = q * NW + ((q & 1) ? NW - 1 - warp : warp);
-        if (q * NW >= nrt) break;
-        if (idx >= nrt) continue;
-        const int rt = nrt - 1 - idx;
-        const int irow = kCholNb + 8 * rt + g;              // panel-relative row held by this lane's A fragment
-        const double *ap = P + min(irow, rows - 1) * kPS2 + t4;
-        double af[8];
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) af[ks] = -ap[4 * ks];
-        const int gi = J + irow;
-        const int ctmax = min(rt, nct - 1);
-        for (int ct = 0; ct <= ctmax; ++ct) {
-          const int crow = kCholNb + 8 * ct + g;            // B fragment: column index n = g → row crow of P
-          const double *bp = P + min(crow, rows - 1) * kPS2 + t4;
-          const int gc = J + kCholNb + 8 * ct + 2 * t4;     // C fragment columns gc, gc+1 of row gi
-          const bool ok = (gi < R1) && (gc < r);
-          const int cbk = gc >> 5;
-          double *cp = A + chol_panel_off(R1, min(cbk, nblk - 1)) + (gi - cbk * kCholNb) * kPS2 + (gc & 31);
-          double c0 = 0.0, c1 = 0.0;
-          if (ok) { const double2 cv = *reinterpret_cast<const double2 *>(cp); c0 = cv.x; c1 = cv.y; }
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) dmma884(c0, c1, af[ks], bp[4 * ks], c0, c1);
-          if (ok) {
-            if (gc + 1 < r) *reinterpret_cast<double2 *>(cp) = make_double2(c0, c1);
-            else cp[0] = c0;
-          }
-        }
-      }
-    }
+    // ---- phase 3: the panel's update of block column b+1 only (what the next diagonal block and its rows need);
+    //      the rest of the trailing matrix is updated in the shadow of the next factorisation (phase 1) ------------
+    chol_trailing(A, tab, P, lda, J, R1, r, 0, 3, warp, NW, lane);
     __syncthreads();
     REKF_TSTAMP();
   }
-  // inverse of the last diagonal block (identity-padded past jb), all warps
-  {
-    const int b = nblk - 1, jb = r - b * kCholNb;
-    invert_diag_block(A + chol_panel_off(R1, b), jb, Dinv + (size_t)b * kCholNb * kCholNb, warp, NW, lane);
+  if (jb_last < kCholNb && tid < jb_last) {                  // ν of the padded last block back to its own row
+    double *col = A + chol_col_off(R1, nblk - 1) + tid * chol_lda(R1, nblk - 1);
+    col[jb_last] = col[kCholNb];
   }
 
-  // ---- publish L (k_solve_w3 reads it from global / L2): warp per column, lanes over rows -------------------
-  for (int c = warp; c < r; c += NW) {
-    const int b = c >> 5, jj = c & 31, base = b << 5;
-    const double *P = A + chol_panel_off(R1, b) + jj;
-    double *dst = Sb + (size_t)c * sld;
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = base + lane + 32 * u;
-      v[u] = (i < R1) ? P[(min(i, R1 - 1) - base) * kPS2] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int i = base + lane + 32 * u;
-      if (i >= c && i < R1) dst[i] = v[u];
-    }
+  // ---- publish L (k_solve_w3 reads it from global / L2): the same per-column bulk copies, the other way ---------------
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the panels → visible to the bulk engine
+  __syncthreads();
+  if (col_bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   REKF_TSTAMP();
+#ifdef REKF_CHOL_TIMING
+  if (lane == 0) tlog[64 + warp] = (double)clock64();       // per-warp finish stamps
+#endif
   if (bad && lane == 0) atomicOr(&st.flags, FLAG_NOT_SPD);
 }
 

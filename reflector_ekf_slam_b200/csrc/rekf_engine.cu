@@ -222,8 +222,21 @@ int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
   }
   {
     ProfScope p(h, K_CHOL, stream);
-    if (h->chol_resident) k_cholesky_smem<<<L.Sg, kCholSmemThreads, smem_chol_resident(L.rcap), stream>>>(L);
-    else k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
+    if (h->chol_resident) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * L.Sg);
+      cfg.blockDim = dim3(kCholSmemThreads);
+      cfg.dynamicSmemBytes = smem_chol_resident(L.rcap);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CK(cudaLaunchKernelEx(&cfg, k_cholesky_smem, L));
+    } else {
+      k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
+    }
   }
   {
     ProfScope p(h, K_SOLVE, stream);
