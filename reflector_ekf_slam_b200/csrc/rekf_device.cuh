@@ -96,7 +96,8 @@ struct Layout {
   double *Dinv;   // [S][rld/32][32][32] inverses of L's diagonal blocks
   float *Wt_hi, *Wt_lo;  // [S][ld][rld] tf32 hi/lo split of Wᵀ (K-major operands of the tcgen05 SYRK)
   double *W64;    // [S][ld][rld] fp64 Wᵀ (REKF_COV_SIMT_F64 only, else nullptr)
-  int8_t *Wq;     // [S][4][ld][kq] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4)
+  int8_t *Wq;     // [S][4][kq/64][ld][64] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4), K in
+                  // 64-byte chunks OUTSIDE the row index: a TMA box of 128 rows x 64 K-bytes is one contiguous 8 KB block
   int *Wexp;      // [S][ld] per-row power-of-two exponent e_c of Wq
   double *Wscale; // [S][ld] 2^e_c as a double (what the SYRK epilogue multiplies by)
   int kq;         // round_up(rcap, 64): K extent of Wq in bytes
@@ -108,6 +109,10 @@ struct Layout {
 };
 
 __host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }
+// byte offset of digit slice p, state slot `row`, measurement byte `kbyte` in Layout::Wq
+__host__ __device__ inline size_t wq_offset(const Layout &L, int s, int p, int row, int kbyte) {
+  return ((((size_t)s * 4 + p) * (L.kq >> 6) + (kbyte >> 6)) * L.ld + row) * 64 + (kbyte & 63);
+}
 __host__ __device__ inline int internal_dim(int N) { return kPoseSlots + 2 * N; }
 
 }  // namespace rekf

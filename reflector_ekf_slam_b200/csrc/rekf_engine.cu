@@ -92,9 +92,7 @@ struct rekf_handle {
   // tcgen05 SYRK resources
   bool chol_resident = false, solve_w2 = false;
   SyrkTc tc{};
-  SyrkI8 tc8{};
   SyrkI8P tc8p{};
-  bool persistent_syrk = true;
   std::vector<void *> allocations;
 };
 
@@ -254,7 +252,7 @@ int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
       ++h->launches;                                              // two kernels inside this scope
       SyrkI8P tc8p = h->tc8p;
       if (&grp == &h->whole) tc8p.reserve_sms = 0;                // nothing else is running beside the whole batch
-      int rc = h->persistent_syrk ? syrk_i8p_launch(tc8p, L, stream) : syrk_i8_launch(h->tc8, L, stream);
+      int rc = syrk_i8p_launch(tc8p, L, stream);
       if (rc != 0) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     } else {
       int rc = syrk_tc_launch(h->tc, L, stream);
@@ -508,9 +506,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK setup failed: %s", why);
   }
   if (opts->cov_update == REKF_COV_TCGEN05_I8X4) {
-    h->persistent_syrk = std::getenv("REKF_SYRK_NONPERSISTENT") == nullptr;
-    const char *why = syrk_i8_init(h->tc8, L);
-    if (!why) why = syrk_i8p_init(h->tc8p, L);
+    const char *why = syrk_i8p_init(h->tc8p, L);
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK setup failed: %s", why);
     // with several groups in flight the persistent kernel leaves a few SMs to the other groups' narrow kernels
     h->tc8p.reserve_sms = G > 1 ? (opts->syrk_reserve_sms > 0 ? opts->syrk_reserve_sms : 2 * ((sessions + G - 1) / G) + 4) : 0;

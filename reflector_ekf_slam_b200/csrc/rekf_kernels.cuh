@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
       }
 #pragma unroll
       for (int p = 0; p < 4; ++p)
-        *reinterpret_cast<uint32_t *>(L.Wq + (((size_t)s * 4 + p) * ld + c0 + cc) * L.kq + k0) = packed[p];
+        *reinterpret_cast<uint32_t *>(L.Wq + wq_offset(L, s, p, c0 + cc, k0)) = packed[p];
     }
   } else if (L.Wt_hi) {
     float *Wh = L.Wt_hi + (size_t)s * ld * rld, *Wl = L.Wt_lo + (size_t)s * ld * rld;

@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
         const int row = e >> 4, j = (e & 15) * 4;
         if (j < ng) {                                  // kq is a multiple of 64 bytes: ng is a multiple of 16 words
           const int p = row >> 5, cc = row & 31;
-          uint32_t *dst = reinterpret_cast<uint32_t *>(L.Wq + (((size_t)s * 4 + p) * ld + c0 + cc) * L.kq) + g0 + j;
+          uint32_t *dst = reinterpret_cast<uint32_t *>(L.Wq + wq_offset(L, s, p, c0 + cc, 4 * (g0 + j)));
           *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(Qs + row * kQP + j);
         }
       }

@@ -21,13 +21,35 @@
 
 namespace rekf {
 
-constexpr int kPThreads = 384;                           // 12 warps: 8 epilogue, operand TMA, MMA, Σ load, Σ store
+constexpr int kPEpiWarps = 16;                           // epilogue warps: warp w owns TMEM lanes 32·(w%4).. and 8 of each half-tile's 32 columns
+constexpr int kPThreads = (kPEpiWarps + 4) * 32;         // + operand TMA, MMA, Σ load, Σ store
 constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ: 128 rows x 32 columns fp64 = 32 KB
 constexpr int kPSigSlots = 4;                            // Σ half-tile ring: two whole tiles, so loads run a full tile ahead
-constexpr int kPMaxSess = 64;                           // sessions whose (r, n) are cached in shared memory
+constexpr int kPMaxSess = 32;                           // sessions whose (r, n) are cached in shared memory
 constexpr int kPQ = 4;                                   // work-item ring entries
+// Operand ring: K = 32 per stage (one MMA k-step, 32-byte swizzle), FOUR stages.  The kernel was operand-latency bound
+// with two 64-K stages (ncu: the epilogue warps' top stall was the wait for acc_full): only one 48 KB load could be in
+// flight while the other stage was consumed; now three 24 KB loads are.
+#ifndef REKF_SYRK_KBOX
+#define REKF_SYRK_KBOX 64
+#endif
+constexpr int kPKBox = REKF_SYRK_KBOX;                   // 32 (32-byte swizzle, 4 stages) or 64 (64-byte swizzle, 2 stages)
+constexpr int kPBoxA = 128 * kPKBox;                     // 4 KB
+constexpr int kPBoxB = kI8TileN * kPKBox;                // 2 KB
+constexpr int kPStageBytes = kI8Slices * (kPBoxA + kPBoxB);   // 24 KB
+constexpr int kPStages = 128 / kPKBox;
 // operand ring + Σ ring + alignment slack + barriers + [2][64] column scales + [2][64] column flags + session table
-constexpr int kPSmemBytes = kI8Stages * kI8StageBytes + kPSigSlots * kPSigHalf + 1024 + 256 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8 + 64;
+constexpr int kPSmemBytes = kPStages * kPStageBytes + kPSigSlots * kPSigHalf + 1024 + 512 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8 + 64;
+// K-major, SWIZZLE_32B: rows of 32 bytes, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                               // SWIZZLE_32B
+  return d;
+}
 
 struct SyrkI8P {
   CUtensorMap map_a, map_b, map_sig;
@@ -54,7 +76,9 @@ __device__ __forceinline__ bool mbar_wait_backoff(uint64_t *bar, uint32_t parity
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return true;
+#ifndef REKF_SYRK_NOSLEEP
     __nanosleep(64);
+#endif
   }
   return false;
 }
@@ -68,15 +92,15 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
                    const __grid_constant__ CUtensorMap map_sig) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *ops = base;                                   // [2][48 KB] int8 slice boxes
-  uint8_t *sig = base + kI8Stages * kI8StageBytes;       // [4][32 KB] Σ half-tiles
+  uint8_t *ops = base;                                   // [4][24 KB] int8 slice boxes
+  uint8_t *sig = base + kPStages * kPStageBytes;         // [4][32 KB] Σ half-tiles
   uint64_t *bars = reinterpret_cast<uint64_t *>(sig + kPSigSlots * kPSigHalf);
-  uint64_t *op_full = bars, *op_empty = bars + 2, *acc_full = bars + 4, *acc_empty = bars + 6, *sig_full = bars + 8,
-           *sig_empty = bars + 12, *sig_done = bars + 16;
-  uint64_t *sc_full = bars + 20;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 22);
-  uint64_t *q_full = bars + 23, *q_empty = bars + 27;                                      // work-item ring
-  double *sc_tab = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(bars) + 256);   // [2][64] Wscale of the tile's columns
+  uint64_t *op_full = bars, *op_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10, *sig_full = bars + 12,
+           *sig_empty = bars + 16, *sig_done = bars + 20;
+  uint64_t *sc_full = bars + 24;
+  uint64_t *q_full = bars + 26, *q_empty = bars + 30;                                      // work-item ring
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 34);
+  double *sc_tab = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(bars) + 512);   // [2][64] Wscale of the tile's columns
   unsigned char *fl_tab = reinterpret_cast<unsigned char *>(sc_tab + 2 * 64);             // [2][64] Wflag of the tile's columns
   int *sess_r = reinterpret_cast<int *>(fl_tab + 2 * 64);                                  // [kPMaxSess] r, 0 = nothing to do
   int *sess_n = sess_r + kPMaxSess;                                                        // [kPMaxSess] internal dimension
@@ -92,16 +116,14 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   const int tiles = (L.ld / 128) * (L.ld / 128 + 1);
   const int total = tiles * L.Sg;
 
-  if (warp == 8) {
+  if (warp == kPEpiWarps) {
     if (lane == 0) {
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&op_full[i], 1); mbar_init(&op_empty[i], 1);
-        mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); mbar_init(&sc_full[i], 1);
-      }
+      for (int i = 0; i < kPStages; ++i) { mbar_init(&op_full[i], 1); mbar_init(&op_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPEpiWarps * 32); mbar_init(&sc_full[i], 1); }
       for (int i = 0; i < kPSigSlots; ++i) {
-        mbar_init(&sig_full[i], 1); mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], 256);
+        mbar_init(&sig_full[i], 1); mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], kPEpiWarps * 32);
       }
-      for (int i = 0; i < kPQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 11); }   // 11 consumer warps
+      for (int i = 0; i < kPQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], kPEpiWarps + 3); }   // consumer warps
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -141,7 +163,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     return item;
   };
 
-  if (warp == 8) {
+  if (warp == kPEpiWarps) {
     // ===== operand TMA producer =====
     if (lane == 0) {
       uint32_t kbc = 0;
@@ -156,21 +178,20 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         mbar_arrive(&q_full[slot]);
         if (item >= total) break;
         nxt = atomicAdd(L.tile_counter, 1);
-        const int nkb = (r + kI8KBox - 1) / kI8KBox;
+        const int nkb = (r + kPKBox - 1) / kPKBox;
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-          const int stage = kbc & 1;
-          if (!mbar_wait_backoff(&op_empty[stage], ((kbc >> 1) & 1) ^ 1)) { timeout = true; break; }
-          uint8_t *sa = ops + (size_t)stage * kI8StageBytes, *sb = sa + kI8Slices * kI8BoxA;
-          mbar_expect_tx(&op_full[stage], kI8Slices * (kI8BoxA + (inA ? 0 : kI8BoxB)));
-#pragma unroll
-          for (int p = 0; p < kI8Slices; ++p) {
-            tma_load_4d(sa + p * kI8BoxA, &map_a, &op_full[stage], kb * kI8KBox, i0, p, s);
-            if (!inA) tma_load_4d(sb + p * kI8BoxB, &map_b, &op_full[stage], kb * kI8KBox, j0, p, s);
-          }
+          const int stage = kbc & (kPStages - 1);
+          if (!mbar_wait_backoff(&op_empty[stage], ((kbc / kPStages) & 1) ^ 1)) { timeout = true; break; }
+          uint8_t *sa = ops + (size_t)stage * kPStageBytes, *sb = sa + kI8Slices * kPBoxA;
+          mbar_expect_tx(&op_full[stage], kI8Slices * (kPBoxA + (inA ? 0 : kPBoxB)));
+          // one box per operand: all four digit slices ride in the box's third dimension (a single thread issues
+          // these, and eight small boxes per stage made the issue rate the bottleneck)
+          tma_load_5d(sa, &map_a, &op_full[stage], 0, i0, kb, 0, s);
+          if (!inA) tma_load_5d(sb, &map_b, &op_full[stage], 0, j0, kb, 0, s);
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kPEpiWarps + 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       uint32_t kbc = 0, iter = 0;
@@ -183,15 +204,15 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
         tc_fence_after();
         const uint32_t acc = tmem + set * 256;
-        const int nkb = (r + kI8KBox - 1) / kI8KBox, nk32 = (r + 31) / 32;
+        const int nkb = (r + kPKBox - 1) / kPKBox;
         for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-          const int stage = kbc & 1;
-          if (!mbar_wait_backoff(&op_full[stage], (kbc >> 1) & 1)) { timeout = true; break; }
+          const int stage = kbc & (kPStages - 1);
+          if (!mbar_wait_backoff(&op_full[stage], (kbc / kPStages) & 1)) { timeout = true; break; }
           tc_fence_after();
-          const uint32_t sa = smem_u32(ops + (size_t)stage * kI8StageBytes);
-          const uint32_t sb = inA ? sa + (uint32_t)(j0 - i0) * kI8KBox : sa + kI8Slices * kI8BoxA;
-          const uint32_t bstride = inA ? kI8BoxA : kI8BoxB;
-          const int steps = min(2, nk32 - kb * 2);
+          const uint32_t sa = smem_u32(ops + (size_t)stage * kPStageBytes);
+          const uint32_t sb = inA ? sa + (uint32_t)(j0 - i0) * kPKBox : sa + kI8Slices * kPBoxA;
+          const uint32_t bstride = inA ? kPBoxA : kPBoxB;
+          const int steps = min(kPKBox / 32, (r + 31) / 32 - kb * (kPKBox / 32));
           for (int ks = 0; ks < steps; ++ks) {
             const uint32_t koff = ks * 32;
             const bool first = (kb | ks) == 0;
@@ -200,8 +221,9 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
 #pragma unroll
               for (int p = 0; p <= sgrp; ++p) {
                 const int q = sgrp - p;
-                tc_mma_i8(acc + sgrp * kI8TileN, make_kmajor_sw64_desc(sa + p * kI8BoxA + koff),
-                          make_kmajor_sw64_desc(sb + q * bstride + koff), kIdescI8, (first && p == 0) ? 0u : 1u);
+                const uint32_t aa = sa + p * kPBoxA + koff, bb = sb + q * bstride + koff;
+                tc_mma_i8(acc + sgrp * kI8TileN, kPKBox == 32 ? make_kmajor_sw32_desc(aa) : make_kmajor_sw64_desc(aa),
+                          kPKBox == 32 ? make_kmajor_sw32_desc(bb) : make_kmajor_sw64_desc(bb), kIdescI8, (first && p == 0) ? 0u : 1u);
               }
             }
           }
@@ -211,7 +233,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         ++iter;
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == kPEpiWarps + 2) {
     // ===== column scales / flags of every tile → shared memory (whole warp); Σ-tile TMA loads (lane 0, tiles strictly
     //       above the diagonal).  The scale slot is the accumulator set's: free once the epilogue released that set. =====
     uint32_t sit = 0, iter = 0;
@@ -247,7 +269,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       ++iter;
       if (!inA) ++sit;
     }
-  } else if (warp == 11) {
+  } else if (warp == kPEpiWarps + 3) {
     // ===== Σ-tile TMA store: waits until the 256 epilogue threads have rewritten a half-tile, stores it, frees it =====
     if (lane == 0) {
       uint32_t sit = 0;
@@ -271,9 +293,11 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all Σ stores landed
     }
-  } else if (warp < 8) {
-    // ===== epilogue: warp w owns TMEM lanes 32·(w%4).. ; within a 32-column half-tile, columns 16·(w/4).. =====
-    const int quad = warp & 3, halfw = warp >> 2;
+  } else if (warp < kPEpiWarps) {
+    // ===== epilogue: warp w owns TMEM lanes 32·(w%4).. ; within a 32-column half-tile, columns 8·(w/4).. .  Sixteen warps
+    //       (four per scheduler) because the per-element chain — TMEM load, integer recombination, int→fp64, scale, FMA —
+    //       is latency-bound: with eight warps the epilogue, not HBM, set the tile period =====
+    const int quad = warp & 3, cgp = warp >> 2;
     const int il = quad * 32 + lane;                     // row inside the tile
     uint32_t iter = 0, sit = 0;
     const int ld = L.ld;
@@ -300,96 +324,94 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       tc_fence_after();
 #pragma unroll 1
       for (int h = 0; h < 2; ++h) {
-        const int col0 = 32 * h + 16 * halfw;            // first of this thread's 16 tile columns
+        const int col0 = 32 * h + 8 * cgp;               // first of this thread's 8 tile columns
         const int jbase = j0 + col0;
         const uint32_t taddr = tmem + set * 256 + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
-        // s32 accumulators of the four digit groups, two loads in flight; groups are recombined pairwise in 32 bits
+        // s32 accumulators of the four digit groups, all four loads in flight; groups are recombined pairwise in 32 bits
         // (|acc| < 2^23 for K <= 512, so acc·2^7 + acc' fits), then once in 64 bits: G = Σ_g acc_g · 2^(7·(3-g))
-        long long G[16];
+        long long G[8];
         {
-          uint32_t ga[16], gb[16];
-          int hi[16];
-          tc_ld16(taddr, ga);
-          tc_ld16(taddr + kI8TileN, gb);
+          uint32_t g0[8], g1[8], g2[8], g3[8];
+          tc_ld8(taddr, g0);
+          tc_ld8(taddr + kI8TileN, g1);
+          tc_ld8(taddr + 2 * kI8TileN, g2);
+          tc_ld8(taddr + 3 * kI8TileN, g3);
           tc_wait_ld();
 #pragma unroll
-          for (int u = 0; u < 16; ++u) hi[u] = ((int)ga[u] << 7) + (int)gb[u];
-          tc_ld16(taddr + 2 * kI8TileN, ga);
-          tc_ld16(taddr + 3 * kI8TileN, gb);
-          tc_wait_ld();
-#pragma unroll
-          for (int u = 0; u < 16; ++u) G[u] = ((long long)hi[u] << 14) + (long long)(((int)ga[u] << 7) + (int)gb[u]);
+          for (int u = 0; u < 8; ++u)
+            G[u] = ((long long)(((int)g0[u] << 7) + (int)g1[u]) << 14) + (long long)(((int)g2[u] << 7) + (int)g3[u]);
         }
-        const uint4 cf = *reinterpret_cast<const uint4 *>(flt + col0);
+        const uint2 cf = *reinterpret_cast<const uint2 *>(flt + col0);
         const double2 *scj = reinterpret_cast<const double2 *>(sct + col0);
-        double cur[16];
+        double cur[8];
         if (!inA) {
           // ---- Σ half-tile staged by TMA: read own row (swizzled 16-byte chunks), update, write back, TMA store ----
           const int slot = ((sit & 1) << 1) | h;
           if (!mbar_wait(&sig_full[slot], (sit >> 1) & 1)) timeout = true;
-          uint8_t *rowp = sig + (size_t)slot * kPSigHalf + (size_t)halfw * (kPSigHalf / 2) + (size_t)il * 128;
+          uint8_t *rowp = sig + (size_t)slot * kPSigHalf + (size_t)(cgp >> 1) * (kPSigHalf / 2) + (size_t)il * 128;
+          const int ch0 = 4 * (cgp & 1);                  // this thread's four 16-byte chunks of the 128-byte row
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const double2 t = *reinterpret_cast<const double2 *>(rowp + ((c ^ (il & 7)) << 4));
+          for (int c = 0; c < 4; ++c) {
+            const double2 t = *reinterpret_cast<const double2 *>(rowp + (((ch0 + c) ^ (il & 7)) << 4));
             cur[2 * c] = t.x; cur[2 * c + 1] = t.y;
           }
-          const bool no_flags = row_ok && (cf.x | cf.y | cf.z | cf.w) == 0u;   // the common case, warp-uniform but for row_ok
+          const bool no_flags = row_ok && (cf.x | cf.y) == 0u;   // the common case, warp-uniform but for row_ok
           if (no_flags) {
 #pragma unroll
-            for (int u = 0; u < 16; u += 2) {
+            for (int u = 0; u < 8; u += 2) {
               const double2 sj = scj[u >> 1];
               cur[u] = fma(-i64_to_f64(G[u]), si * sj.x, cur[u]);
               cur[u + 1] = fma(-i64_to_f64(G[u + 1]), si * sj.y, cur[u + 1]);
             }
           } else if (row_ok) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+            for (int u = 0; u < 8; ++u) {
+              const unsigned cfw = (u < 4) ? cf.x : cf.y;
               if (!((cfw >> (8 * (u & 3))) & 0xffu)) cur[u] = fma(-i64_to_f64(G[u]), si * sct[col0 + u], cur[u]);
             }
           }
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            *reinterpret_cast<double2 *>(rowp + ((c ^ (il & 7)) << 4)) = make_double2(cur[2 * c], cur[2 * c + 1]);
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<double2 *>(rowp + (((ch0 + c) ^ (il & 7)) << 4)) = make_double2(cur[2 * c], cur[2 * c + 1]);
           // mirrored lower-triangle copy straight from registers (lanes = consecutive rows: coalesced)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           mbar_arrive(&sig_done[slot]);                     // hand the half-tile to the store warp
-          if (no_flags && i < n && jbase + 15 < n) {
+          if (no_flags && i < n && jbase + 7 < n) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
+            for (int u = 0; u < 8; ++u) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
           } else if (row_ok && i < n) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+            for (int u = 0; u < 8; ++u) {
+              const unsigned cfw = (u < 4) ? cf.x : cf.y;
               if (jbase + u < n && !((cfw >> (8 * (u & 3))) & 0xffu)) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
             }
           }
         } else {
           // ---- diagonal tile: direct global accesses, element predicates (i <= j), exact diagonal ----
-          const bool want = row_ok && i < n && jbase < n && !(jbase + 15 < i);
+          const bool want = row_ok && i < n && jbase < n && !(jbase + 7 < i);
           if (want) {
             double *row = Sg + (size_t)i * ld + jbase;
-#pragma unroll
-            for (int u = 0; u < 16; u += 4) ldg256(row + u, cur + u);
+            ldg256(row, cur);
+            ldg256(row + 4, cur + 4);
             const int ud = i - jbase;
             double old_diag = 0.0;
 #pragma unroll
-            for (int u = 0; u < 16; u += 2) {
+            for (int u = 0; u < 8; u += 2) {
               const double2 sj = scj[u >> 1];
               if (u == ud) old_diag = cur[u];
               if (u + 1 == ud) old_diag = cur[u + 1];
               cur[u] = fma(-i64_to_f64(G[u]), si * sj.x, cur[u]);
               cur[u + 1] = fma(-i64_to_f64(G[u + 1]), si * sj.y, cur[u + 1]);
             }
-            if (ud >= 0 && ud < 16) {
+            if (ud >= 0 && ud < 8) {
               const double dd = old_diag - L.Wdiag[(size_t)s * ld + i];
 #pragma unroll
-              for (int u = 0; u < 16; ++u) if (u == ud) cur[u] = dd;
+              for (int u = 0; u < 8; ++u) if (u == ud) cur[u] = dd;
             }
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
+            for (int u = 0; u < 8; ++u) {
               const int j = jbase + u;
-              const unsigned cfw = (u < 4) ? cf.x : (u < 8) ? cf.y : (u < 12) ? cf.z : cf.w;
+              const unsigned cfw = (u < 4) ? cf.x : cf.y;
               if (j < n && i <= j && !((cfw >> (8 * (u & 3))) & 0xffu)) {
                 row[u] = cur[u];
                 if (i != j) Sg[(size_t)j * ld + i] = cur[u];
@@ -406,7 +428,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   }
   if (timeout) atomicOr(&L.st[L.s0].flags, FLAG_TCGEN05_TIMEOUT);
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kPEpiWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
   }
@@ -419,16 +441,19 @@ inline const char *syrk_i8p_init(SyrkI8P &tc, const Layout &L) {
       qres != cudaDriverEntryPointSuccess)
     return "cuTensorMapEncodeTiled entry point not available";
   PFN_encodeTiled encode = reinterpret_cast<PFN_encodeTiled>(fn);
-  const cuuint64_t dims[4] = {(cuuint64_t)L.kq, (cuuint64_t)L.ld, (cuuint64_t)kI8Slices, (cuuint64_t)L.S};
-  const cuuint64_t strides[3] = {(cuuint64_t)L.kq, (cuuint64_t)L.ld * L.kq, (cuuint64_t)kI8Slices * L.ld * L.kq};
-  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-  const cuuint32_t box_a[4] = {(cuuint32_t)kI8KBox, 128u, 1u, 1u};
-  const cuuint32_t box_b[4] = {(cuuint32_t)kI8KBox, (cuuint32_t)kI8TileN, 1u, 1u};
-  if (encode(&tc.map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, L.Wq, dims, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+  // Wq is [S][4 slices][kq/64 chunks][ld rows][64 bytes]: a box = 64 K-bytes x rows x 1 chunk x 4 slices, each slice's part contiguous
+  static_assert(kPKBox == 64, "the Wq layout is tiled in 64-byte K chunks");
+  const cuuint64_t nch = (cuuint64_t)(L.kq / 64);
+  const cuuint64_t dims[5] = {64u, (cuuint64_t)L.ld, nch, (cuuint64_t)kI8Slices, (cuuint64_t)L.S};
+  const cuuint64_t strides[4] = {64u, (cuuint64_t)L.ld * 64, nch * L.ld * 64, (cuuint64_t)kI8Slices * nch * L.ld * 64};
+  const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+  const cuuint32_t box_a[5] = {64u, 128u, 1u, (cuuint32_t)kI8Slices, 1u};
+  const cuuint32_t box_b[5] = {64u, (cuuint32_t)kI8TileN, 1u, (cuuint32_t)kI8Slices, 1u};
+  if (encode(&tc.map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, L.Wq, dims, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             kPKBox == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return "cuTensorMapEncodeTiled(Wq, A box) failed";
-  if (encode(&tc.map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, L.Wq, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+  if (encode(&tc.map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, L.Wq, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             kPKBox == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return "cuTensorMapEncodeTiled(Wq, B box) failed";
   const cuuint64_t sdims[3] = {(cuuint64_t)L.ld, (cuuint64_t)L.ld, (cuuint64_t)L.S};
   const cuuint64_t sstrides[2] = {(cuuint64_t)L.ld * sizeof(double), (cuuint64_t)L.ld * L.ld * sizeof(double)};
