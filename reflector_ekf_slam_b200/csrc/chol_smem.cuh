@@ -107,11 +107,9 @@ __device__ __forceinline__ void chol_trailing(double *A, const int *tab, const d
 }
 
 __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L) {
+  timeline_mark(L, 3);
   extern __shared__ __align__(128) double sm_d[];
-  // Launched as clusters of two CTAs of which only rank 0 works: a cluster pair is the two SMs of one TPC, and two
-  // factorisations sharing a TPC run their fp64-bound phases at half speed (measured: phase 2 25k → 40k cycles).
-  if (blockIdx.x & 1) return;
-  const int s = L.s0 + (blockIdx.x >> 1);
+  const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;

@@ -106,8 +106,19 @@ struct Layout {
   int *exact_list;       // [S][kMaxExactSlots] the flagged slots of this frame
   int *step;      // device step counter for replay (one per pipeline group)
   int *tile_counter;  // work-queue head of the persistent SYRK (one per pipeline group; reset by k_syrk_f64)
+  unsigned long long *tlog;  // optional kernel-start timeline (REKF_TIMELINE=1): [0] = entries used, then (globaltimer ns << 12 | kernel id << 8 | first session)
 };
 
+constexpr int kTimelineCap = 1 << 16;
+// one entry per kernel launch: stamped by the first thread of the first block when the kernel starts running
+__device__ __forceinline__ void timeline_mark(const Layout &L, int kernel_id) {
+  if (L.tlog && threadIdx.x == 0 && threadIdx.y == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long k = atomicAdd(L.tlog, 1ULL);
+    if (k + 1 < (unsigned long long)kTimelineCap) L.tlog[k + 1] = (t << 12) | ((unsigned long long)kernel_id << 8) | (unsigned long long)(L.s0 & 255);
+  }
+}
 __host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }
 // byte offset of digit slice p, state slot `row`, measurement byte `kbyte` in Layout::Wq
 __host__ __device__ inline size_t wq_offset(const Layout &L, int s, int p, int row, int kbyte) {

@@ -53,10 +53,13 @@ struct Group {
   int slot = 0;
   InputRef host_in{};
   // replay graph (one step of this group)
-  cudaGraphExec_t step_graph = nullptr;
+  cudaGraphExec_t step_graph = nullptr;     // whole step, or its latency-bound half when the groups are staggered
+  cudaGraphExec_t wide_graph = nullptr;     // staggered groups: the bandwidth-bound half (TRSM, SYRK, augmentation)
   InputRef graph_in{};
-  int64_t step_launches = 0;   // kernel nodes in the captured step graph
+  int64_t step_launches = 0;   // kernel nodes in the captured step graph(s)
   cudaEvent_t done = nullptr;  // join marker
+  cudaEvent_t phase_ev = nullptr;   // recorded when this group's latency-bound half of a step has been issued
+  bool phase_recorded = false;
   // asynchronous pose delivery: pinned ring written by stream-ordered copies
   double *pose_host = nullptr;
   static constexpr int kPoseSlots = 64;
@@ -76,6 +79,7 @@ struct rekf_handle {
   Group whole;                 // every session, on `stream`
   std::vector<Group> groups;   // pipeline groups (empty: `whole` is the only one)
   int64_t pose_ticket = 0;     // asynchronous pose requests issued so far
+  int stagger_mode = 2;        // 0: streams free-running, 1: latency-bound halves alternate, 2: bandwidth-bound halves alternate
   // staging for getters / setters
   double *stage_dev = nullptr;
   size_t stage_elems = 0;
@@ -205,8 +209,28 @@ int launch_odometry(rekf_handle *h, Group &grp, const InputRef &in) {
   return 0;
 }
 
-// HandleObservationMessage as a fixed launch chain; sizes are read on the device.
-int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
+// Two pipeline groups are kept in ANTI-phase: a group may start the latency-bound half of a step (association,
+// innovation, Cholesky: a handful of CTAs) only once the other group has issued its own and moved on to the
+// bandwidth-bound half (TRSM, SYRK: the whole GPU).  Left alone the two streams drift into phase — the timeline
+// (scripts/timeline.py) shows both in TRSM, then both in SYRK — and nothing overlaps.
+inline bool staggered(rekf_handle *h, Group &grp) {
+  return h->stagger_mode != 0 && h->groups.size() == 2 && !h->profiling && &grp != &h->whole;
+}
+int stagger_wait(rekf_handle *h, Group &grp) {
+  if (!staggered(h, grp)) return 0;
+  Group &other = h->groups[&grp == &h->groups[0] ? 1 : 0];
+  if (other.phase_recorded) CK(cudaStreamWaitEvent(grp.stream, other.phase_ev, 0));
+  return 0;
+}
+int stagger_mark(rekf_handle *h, Group &grp) {
+  if (!staggered(h, grp)) return 0;
+  CK(cudaEventRecord(grp.phase_ev, grp.stream));
+  grp.phase_recorded = true;
+  return 0;
+}
+
+// HandleObservationMessage, latency-bound half: Predict + ReflectorMatch + measurement rows, S, Cholesky
+int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
   const Layout &L = grp.L;
   cudaStream_t stream = grp.stream;
   {
@@ -220,22 +244,17 @@ int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
   }
   {
     ProfScope p(h, K_CHOL, stream);
-    if (h->chol_resident) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(2 * L.Sg);
-      cfg.blockDim = dim3(kCholSmemThreads);
-      cfg.dynamicSmemBytes = smem_chol_resident(L.rcap);
-      cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
-      cfg.numAttrs = 1;
-      CK(cudaLaunchKernelEx(&cfg, k_cholesky_smem, L));
-    } else {
-      k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
-    }
+    if (h->chol_resident) k_cholesky_smem<<<L.Sg, kCholSmemThreads, smem_chol_resident(L.rcap), stream>>>(L);
+    else k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
   }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// bandwidth-bound half: W = L⁻¹HΣ and the mean update, Σ −= WᵀW, augmentation
+int launch_obs_wide(rekf_handle *h, Group &grp, const InputRef &in) {
+  const Layout &L = grp.L;
+  cudaStream_t stream = grp.stream;
   {
     ProfScope p(h, K_SOLVE, stream);
     if (h->solve_w2) k_solve_w3<<<dim3(L.ld / kW3Cols, 1, L.Sg), 256, smem_solve_w3(L.rld), stream>>>(L);
@@ -265,6 +284,14 @@ int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
   }
   CK(cudaGetLastError());
   return 0;
+}
+
+// HandleObservationMessage as a fixed launch chain.  The host-message path leaves the two streams free-running: its
+// cadence is set by the host's own launches, and the extra event traffic cost more than the stagger gained (measured).
+int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
+  int rc = launch_obs_narrow(h, grp, in);
+  if (!rc) rc = launch_obs_wide(h, grp, in);
+  return rc;
 }
 
 int stage_reserve(rekf_handle *h, size_t elems) {
@@ -318,6 +345,7 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   std::memset(g.mb_host, 0, g.mb_bytes * Group::kSlots);
   for (int i = 0; i < Group::kSlots; ++i) CK(cudaEventCreateWithFlags(&g.slot_done[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&g.phase_ev, cudaEventDisableTiming));
   CK(cudaMallocHost(&g.pose_host, sizeof(double) * 3 * S * Group::kPoseSlots));
   for (int i = 0; i < Group::kPoseSlots; ++i) CK(cudaEventCreateWithFlags(&g.pose_done[i], cudaEventDisableTiming));
   // kernels index every input by the absolute session: bias the bases by -s0 strides
@@ -340,6 +368,8 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
 
 void destroy_group(Group &g) {
   if (g.step_graph) cudaGraphExecDestroy(g.step_graph);
+  if (g.wide_graph) cudaGraphExecDestroy(g.wide_graph);
+  if (g.phase_ev) cudaEventDestroy(g.phase_ev);
   if (g.mb_host) cudaFreeHost(g.mb_host);
   if (g.pose_host) cudaFreeHost(g.pose_host);
   for (auto &e : g.slot_done) if (e) cudaEventDestroy(e);
@@ -411,6 +441,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   L.s0 = 0;
   L.Sg = sessions;
   int G = opts->pipeline_groups > 1 ? std::min(opts->pipeline_groups, sessions) : 1;
+  if (const char *e = std::getenv("REKF_STAGGER")) h->stagger_mode = std::atoi(e);
   L.Ncap = opts->max_landmarks > 0 ? opts->max_landmarks : 1024;
   L.mcap = opts->max_observations > 0 ? opts->max_observations : 128;
   if (L.mcap > 512) return fail(h, REKF_ERR_BAD_ARGUMENT, "max_observations %d > 512", L.mcap);
@@ -461,6 +492,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   if (opts->cov_update != REKF_COV_SIMT_F64 && (rc = dev_alloc(h, &L.Wdiag, S * L.ld))) return rc;
   if ((rc = dev_alloc(h, &L.step, G + 1))) return rc;
   if ((rc = dev_alloc(h, &L.tile_counter, G + 1))) return rc;
+  if (std::getenv("REKF_TIMELINE") && (rc = dev_alloc(h, &L.tlog, kTimelineCap))) return rc;
 
   // initial state: time, pose (:8-11)
   {
@@ -510,7 +542,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 int8 SYRK setup failed: %s", why);
     // with several groups in flight the persistent kernel leaves a few SMs to the other groups' narrow kernels
     h->tc8p.reserve_sms = G > 1 ? (opts->syrk_reserve_sms > 0 ? opts->syrk_reserve_sms : 2 * ((sessions + G - 1) / G) + 4) : 0;
-    if (const char *e = std::getenv("REKF_SYRK_RESERVE_SMS")) h->tc8p.reserve_sms = G > 1 ? std::atoi(e) : 0;
+  if (const char *e = std::getenv("REKF_SYRK_RESERVE_SMS")) h->tc8p.reserve_sms = G > 1 ? std::atoi(e) : 0;
   }
   if (opts->map_path && opts->map_path[0]) rekf_load_map_txt(h, opts->map_path);   // :36
   CK(cudaStreamSynchronize(h->stream));
@@ -641,17 +673,27 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     const bool same = g.step_graph && std::memcmp(&in, &g.graph_in, sizeof(InputRef)) == 0;
     if (!same) {
       if (g.step_graph) { cudaGraphExecDestroy(g.step_graph); g.step_graph = nullptr; }
-      cudaGraph_t cg = nullptr;
+      if (g.wide_graph) { cudaGraphExecDestroy(g.wide_graph); g.wide_graph = nullptr; }
+      const bool split = staggered(h, g);        // two graphs, so that the stagger events sit between them
       const int64_t before = h->launches;
-      CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
-      int rc = launch_odometry(h, g, in);
-      if (!rc) rc = launch_observation(h, g, in);
-      if (!rc) { ProfScope p(h, K_ADVANCE, g.stream); k_advance_step<<<1, 1, 0, g.stream>>>(g.L.step); }
-      cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
-      if (rc) return rc;
-      if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-      CK(cudaGraphInstantiate(&g.step_graph, cg, 0));
-      cudaGraphDestroy(cg);
+      for (int part = 0; part < (split ? 2 : 1); ++part) {
+        cudaGraph_t cg = nullptr;
+        CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        if (part == 0) {
+          rc = launch_odometry(h, g, in);
+          if (!rc) rc = launch_obs_narrow(h, g, in);
+        }
+        if (!rc && (part == 1 || !split)) {
+          rc = launch_obs_wide(h, g, in);
+          if (!rc) { ProfScope p(h, K_ADVANCE, g.stream); k_advance_step<<<1, 1, 0, g.stream>>>(g.L.step); }
+        }
+        cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
+        if (rc) return rc;
+        if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        CK(cudaGraphInstantiate(part == 0 ? &g.step_graph : &g.wide_graph, cg, 0));
+        cudaGraphDestroy(cg);
+      }
       g.graph_in = in;
       g.step_launches = h->launches - before;    // kernel nodes per step
       h->launches = before;                      // the capture pass itself launched nothing
@@ -662,7 +704,14 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     for (size_t gi = 0; gi < act.size(); ++gi) {
       Group &g = *act[gi];
       if (graphs) {
+        int rc = h->stagger_mode == 1 ? stagger_wait(h, g) : 0;
+        if (rc) return rc;
         CK(cudaGraphLaunch(g.step_graph, g.stream));
+        if (g.wide_graph) {
+          if ((rc = h->stagger_mode == 1 ? stagger_mark(h, g) : stagger_wait(h, g))) return rc;
+          CK(cudaGraphLaunch(g.wide_graph, g.stream));
+          if (h->stagger_mode != 1 && (rc = stagger_mark(h, g))) return rc;
+        }
         h->launches += g.step_launches;
         continue;
       }
@@ -703,6 +752,7 @@ int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, si
   else if (n == "wdiag" && L.Wdiag) { src = L.Wdiag + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
   else if (n == "innov") { src = L.innov + (size_t)session * L.rcap; size = sizeof(double) * L.rcap; }
   else if (n == "qd") { src = L.Qd + (size_t)session * L.rcap; size = sizeof(double) * L.rcap; }
+  else if (n == "tlog" && L.tlog) { src = L.tlog; size = sizeof(unsigned long long) * kTimelineCap; }
   else if (n == "state") { src = L.st + session; size = sizeof(SessionState); }
   else if (n == "mu") { src = L.mu + (size_t)session * L.ld; size = sizeof(double) * L.ld; }
   else if (n == "sigma") { src = L.sigma + (size_t)session * L.ld * L.ld; size = sizeof(double) * L.ld * L.ld; }

@@ -133,6 +133,7 @@ __device__ inline int current_step(const InputRef &in) { return in.step ? *in.st
 
 // HandleOdometryMessage (:208-223): stale drop, latch vt_ BEFORE predicting, predict, set time.
 __global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in) {
+  timeline_mark(L, 0);
   const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const double *msg = in.odom + (size_t)s * in.odom_ss + (size_t)current_step(in) * 4;
@@ -161,6 +162,7 @@ __device__ inline void warp_argmin(double &d, int &j) {
 constexpr int kMatchNew = 0, kMatchState = 1, kMatchMap = 2;
 
 __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in) {
+  timeline_mark(L, 1);
   extern __shared__ int sm_i[];
   const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
 // S = H·Σ·Hᵀ + Q (lower triangle) and the ν row
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_innovation(Layout L) {
+  timeline_mark(L, 2);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
@@ -687,6 +690,7 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
 // Σ −= Wᵀ·W on the fp64 pipe: 64x64 upper-triangular tiles, mirrored (exact symmetry by construction)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
+  timeline_mark(L, 5);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   if (L.tile_counter && blockIdx.x == 0 && blockIdx.z == 0 && threadIdx.x == 0) *L.tile_counter = 0;   // queue head of the next launch
@@ -750,6 +754,7 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
 // augmentation (:311-364) + end-of-step bookkeeping
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
+  timeline_mark(L, 7);
   const int s = L.s0 + blockIdx.z;
   SessionState &st = L.st[s];
   const int t_idx = current_step(in);

@@ -32,6 +32,7 @@ inline size_t smem_solve_w3(int rld) {
 __device__ __forceinline__ int swz(int row) { return ((row & 3) << 2) | ((row >> 2) & 3); }
 
 __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
+  timeline_mark(L, 4);
   extern __shared__ double sm_d[];
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];

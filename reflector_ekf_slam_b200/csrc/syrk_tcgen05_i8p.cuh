@@ -90,6 +90,7 @@ __device__ __forceinline__ double i64_to_f64(long long g) {
 __global__ void __launch_bounds__(kPThreads, 1)
 k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_sig) {
+  timeline_mark(L, 6);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *ops = base;                                   // [4][24 KB] int8 slice boxes
