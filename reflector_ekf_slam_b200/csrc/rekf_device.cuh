@@ -61,6 +61,7 @@ struct InputRef {
   long long odom_ss, time_ss, xy_ss;
   int m_stride, m_fixed;
   const int *step;          // device step counter, nullptr -> 0
+  int fuse_odom;            // replay: k_observation_front handles the step's odometry message first (no k_odometry launch)
   double *pose_out;         // optional: pose after the step, pose_out + s*pose_ss + t*3
   long long pose_ss;
 };
@@ -106,6 +107,7 @@ struct Layout {
   int *exact_list;       // [S][kMaxExactSlots] the flagged slots of this frame
   int *step;      // device step counter for replay (one per pipeline group)
   int *tile_counter;  // work-queue head of the persistent SYRK (one per pipeline group; reset by k_syrk_f64)
+  unsigned *step_ticket;  // blocks of k_augment that have finished (one per pipeline group): the last one advances `step`
   unsigned long long *tlog;  // optional kernel-start timeline (REKF_TIMELINE=1): [0] = entries used, then (globaltimer ns << 12 | kernel id << 8 | first session)
 };
 

@@ -28,9 +28,9 @@ using namespace rekf;
 
 namespace {
 
-enum KernelId { K_ODOM = 0, K_FRONT, K_INNOV, K_CHOL, K_SOLVE, K_SYRK, K_AUGMENT, K_ADVANCE, K_COUNT };
+enum KernelId { K_ODOM = 0, K_FRONT, K_INNOV, K_CHOL, K_SOLVE, K_SYRK, K_AUGMENT, K_COUNT };
 const char *kKernelNames[K_COUNT] = {"k_odometry", "k_observation_front", "k_innovation", "k_cholesky",
-                                     "k_solve_w", "k_syrk", "k_augment", "k_advance_step"};
+                                     "k_solve_w", "k_syrk", "k_augment"};
 
 struct ProfRecord { int id; cudaEvent_t a, b; };
 
@@ -331,6 +331,7 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   g.L.Sg = Sg;
   g.L.step = h->L.step + index;
   g.L.tile_counter = h->L.tile_counter + index;
+  g.L.step_ticket = h->L.step_ticket + index;
   const size_t S = (size_t)Sg;
   const Layout &L = h->L;
   g.off_odom = 0;
@@ -361,6 +362,7 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   in.m_stride = L.mcap;
   in.m_fixed = 0;
   in.step = nullptr;
+  in.fuse_odom = 0;
   in.pose_out = nullptr;
   in.pose_ss = 0;
   return 0;
@@ -492,6 +494,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   if (opts->cov_update != REKF_COV_SIMT_F64 && (rc = dev_alloc(h, &L.Wdiag, S * L.ld))) return rc;
   if ((rc = dev_alloc(h, &L.step, G + 1))) return rc;
   if ((rc = dev_alloc(h, &L.tile_counter, G + 1))) return rc;
+  if ((rc = dev_alloc(h, &L.step_ticket, G + 1))) return rc;
   if (std::getenv("REKF_TIMELINE") && (rc = dev_alloc(h, &L.tlog, kTimelineCap))) return rc;
 
   // initial state: time, pose (:8-11)
@@ -666,6 +669,7 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     in.m_stride = m;
     in.m_fixed = m;
     in.step = g.L.step;
+    in.fuse_odom = 1;
     in.pose_out = static_cast<double *>(d_pose_out);
     in.pose_ss = (long long)T * 3;
     CK(cudaMemsetAsync(g.L.step, 0, sizeof(int), g.stream));
@@ -680,14 +684,8 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
         cudaGraph_t cg = nullptr;
         CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
         int rc = 0;
-        if (part == 0) {
-          rc = launch_odometry(h, g, in);
-          if (!rc) rc = launch_obs_narrow(h, g, in);
-        }
-        if (!rc && (part == 1 || !split)) {
-          rc = launch_obs_wide(h, g, in);
-          if (!rc) { ProfScope p(h, K_ADVANCE, g.stream); k_advance_step<<<1, 1, 0, g.stream>>>(g.L.step); }
-        }
+        if (part == 0) rc = launch_obs_narrow(h, g, in);      // k_observation_front takes the odometry message too
+        if (!rc && (part == 1 || !split)) rc = launch_obs_wide(h, g, in);   // k_augment advances the step counter
         cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
         if (rc) return rc;
         if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
@@ -715,11 +713,8 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
         h->launches += g.step_launches;
         continue;
       }
-      int rc = launch_odometry(h, g, ins[gi]);
+      int rc = launch_observation(h, g, ins[gi]);
       if (rc) return rc;
-      if ((rc = launch_observation(h, g, ins[gi]))) return rc;
-      ProfScope p(h, K_ADVANCE, g.stream);
-      k_advance_step<<<1, 1, 0, g.stream>>>(g.L.step);
     }
   }
   CK(cudaGetLastError());

@@ -132,19 +132,23 @@ __device__ inline void predict_cta(const Layout &L, int s, double dt) {
 __device__ inline int current_step(const InputRef &in) { return in.step ? *in.step : 0; }
 
 // HandleOdometryMessage (:208-223): stale drop, latch vt_ BEFORE predicting, predict, set time.
-__global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in) {
-  timeline_mark(L, 0);
-  const int s = L.s0 + blockIdx.x;
+__device__ inline void odometry_cta(const Layout &L, int s, const InputRef &in) {
   SessionState &st = L.st[s];
   const double *msg = in.odom + (size_t)s * in.odom_ss + (size_t)current_step(in) * 4;
   const double time = msg[0];
   const double t_state = st.time;
   __syncthreads();
-  if (time < t_state) return;                      // :211
+  if (time < t_state) return;                      // :211 (block-uniform)
   if (threadIdx.x == 0) { st.vt[0] = msg[1]; st.vt[1] = msg[2]; st.vt[2] = msg[3]; }   // :216
   __syncthreads();
   predict_cta(L, s, time - t_state);               // :217-218
   if (threadIdx.x == 0) st.time = time;            // :219
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in) {
+  timeline_mark(L, 0);
+  odometry_cta(L, L.s0 + blockIdx.x, in);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -165,6 +169,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   timeline_mark(L, 1);
   extern __shared__ int sm_i[];
   const int s = L.s0 + blockIdx.x;
+  if (in.fuse_odom) odometry_cta(L, s, in);        // replay: this step's HandleOdometryMessage first
   SessionState &st = L.st[s];
   const int t_idx = current_step(in);
   const double time = in.obs_time[(size_t)s * in.time_ss + t_idx];
@@ -842,10 +847,15 @@ __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
       o[0] = mu[0]; o[1] = mu[1]; o[2] = mu[2];
     }
   }
+  // replay: the last block of the whole launch advances the step counter (every block has read it by now)
+  if (in.step && threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(L.step_ticket, 1u) == gridDim.x * gridDim.z - 1) {
+      *L.step_ticket = 0;
+      *const_cast<int *>(in.step) += 1;
+    }
+  }
 }
-
-// advances the replay step counter (own launch: every block of the step has read it by now)
-__global__ void k_advance_step(int *step) { *step += 1; }
 
 // ---------------------------------------------------------------------------------------------
 // layout conversion at the C-ABI boundary (reference order ↔ internal slots)
