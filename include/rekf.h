@@ -164,6 +164,10 @@ REKF_API int rekf_batch_fetch_poses(rekf_handle *h, int64_t ticket, double *pose
  * (0,0),(0,1),(1,0),(1,1) per landmark like the save format. */
 REKF_API int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, int cap,
                                 int *count_out);
+/* Node::ReflectorToRosMarkers (ros_node.cc:736-789) evaluated on the device: 5 doubles per landmark — x, y, ellipse
+ * angle, x_len, y_len of the 95 % covariance ellipse (2*sqrt(eigenvalue*5.991), :763-764), major axis first — so the node
+ * can publish its markers without pulling Sigma to the host.  Copies min(N, cap) landmarks, returns N via *count_out. */
+REKF_API int rekf_get_markers(rekf_handle *h, int session, double *markers, int cap, int *count_out);
 /* GetCoviarance() (reflector_ekf_slam.h:29-32): full n x n, column-major, leading dimension ld >= n. */
 REKF_API int rekf_get_sigma(rekf_handle *h, int session, double *sigma, int ld);
 /* ReflectorMatchResult of the last observation frame (ekf_slam_interface.h:18-26); pairs are

@@ -868,6 +868,21 @@ int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, 
   return REKF_OK;
 }
 
+int rekf_get_markers(rekf_handle *h, int session, double *markers, int cap, int *count_out) {
+  if (!h) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  if (count_out) *count_out = st.N;
+  const int c = std::min(st.N, cap);
+  if (c <= 0 || !markers) return REKF_OK;
+  if ((rc = stage_reserve(h, (size_t)st.N * 5))) return rc;
+  k_pack_markers<<<(st.N + 255) / 256, 256, 0, h->stream>>>(h->L, session, h->stage_dev);
+  CK(cudaMemcpyAsync(markers, h->stage_dev, sizeof(double) * 5 * c, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return REKF_OK;
+}
+
 int rekf_get_sigma(rekf_handle *h, int session, double *sigma, int ld) {
   if (!h || !sigma) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;

@@ -886,6 +886,26 @@ __global__ void k_pack_landmarks(Layout L, int s, double *xy, double *cov) {
   cov[4 * j + 0] = Sg[(size_t)a * L.ld + a];       cov[4 * j + 1] = Sg[(size_t)a * L.ld + a + 1];
   cov[4 * j + 2] = Sg[(size_t)(a + 1) * L.ld + a]; cov[4 * j + 3] = Sg[(size_t)(a + 1) * L.ld + a + 1];
 }
+// Node::ReflectorToRosMarkers (ros_node.cc:736-789) on the device: per landmark the mean and the 95 % covariance ellipse
+// (chi-square 5.991, :763-764) of its 2x2 block.  The reference takes the eigen-decomposition from Eigen::EigenSolver,
+// whose eigenvalue order and eigenvector sign are implementation details; here the symmetric 2x2 problem is solved in
+// closed form with the major axis first, which describes the same ellipse.  out[5j..] = x, y, angle, x_len, y_len.
+__global__ void k_pack_markers(Layout L, int s, double *out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= L.st[s].N) return;
+  const int a = kPoseSlots + 2 * j;
+  const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  const double *mu = L.mu + (size_t)s * L.ld;
+  const double sxx = Sg[(size_t)a * L.ld + a], sxy = Sg[(size_t)a * L.ld + a + 1], syy = Sg[(size_t)(a + 1) * L.ld + a + 1];
+  const double mean = 0.5 * (sxx + syy), diff = 0.5 * (sxx - syy);
+  const double rad = hypot(diff, sxy);
+  const double l1 = mean + rad, l2 = mean - rad;             // l1 >= l2
+  out[5 * j + 0] = mu[a];
+  out[5 * j + 1] = mu[a + 1];
+  out[5 * j + 2] = 0.5 * atan2(2.0 * sxy, sxx - syy);        // direction of the l1 eigenvector (:762)
+  out[5 * j + 3] = 2.0 * sqrt(l1 * 5.991);                   // :763
+  out[5 * j + 4] = 2.0 * sqrt(l2 * 5.991);                   // :764
+}
 // in: mu (n_ref), sigma n_ref x n_ref column-major (ld_in).  Symmetrised on the way in: (Σ+Σᵀ)/2.
 __global__ void k_unpack_state(Layout L, int s, const double *mu_in, const double *sig_in, int ld_in, int n_ref) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "rekf_predict_state", "rekf_set_state", "rekf_set_map", "rekf_get_map", "rekf_load_map_txt", "rekf_save_map_txt",
     "rekf_sync", "rekf_stream", "rekf_timer_start", "rekf_timer_stop", "rekf_profile_enable", "rekf_profile_read",
     "rekf_launch_count", "rekf_device_error_flags", "rekf_debug_copy", "rekf_batch_request_poses", "rekf_batch_fetch_poses",
+    "rekf_get_markers",
 ]
 
 
@@ -87,6 +88,7 @@ def load_library(path=None):
         "rekf_debug_copy": (i, [vp, i, C.c_char_p, vp, C.c_size_t]),
         "rekf_batch_request_poses": (i, [vp, P(C.c_int64)]),
         "rekf_batch_fetch_poses": (i, [vp, C.c_int64, vp]),
+        "rekf_get_markers": (i, [vp, i, vp, i, P(i)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -204,6 +206,15 @@ class EKFBatch:
         if N:
             self._ck(self.lib.rekf_get_landmarks(self.h, s, _ptr(xy), _ptr(cov), N, C.byref(cnt)))
         return xy, cov
+
+    def markers(self, s=0):
+        """(N, 5): x, y, angle, x_len, y_len of each landmark's 95 % covariance ellipse (ros_node.cc:736-789)."""
+        cnt = C.c_int()
+        self._ck(self.lib.rekf_get_markers(self.h, s, None, 0, C.byref(cnt)))
+        out = np.zeros((cnt.value, 5))
+        if cnt.value:
+            self._ck(self.lib.rekf_get_markers(self.h, s, _ptr(out), cnt.value, C.byref(cnt)))
+        return out
 
     def sigma(self, s=0):
         n = self.dim(s)

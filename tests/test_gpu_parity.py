@@ -178,6 +178,17 @@ def test_predict_state_and_accessors(engine_lib):
     assert np.abs(pose - orc.GetStateVector()[:3]).max() < MU_TOL_M and rel_fro(cov, S[:3, :3]) < SIGMA_REL_FRO
     xy, blocks = ekf.landmarks()
     assert xy.shape == (16, 2) and rel_fro(blocks[3], S[9:11, 9:11]) < SIGMA_REL_FRO
+    # device-side marker extraction (ros_node.cc:736-789): the 95 % ellipse of every landmark's 2x2 block, checked
+    # against numpy's symmetric eigen-decomposition of the oracle's covariance, and as a reconstruction of the block
+    mk = ekf.markers()
+    assert mk.shape == (16, 5) and np.array_equal(mk[:, :2], xy)
+    for j in range(16):
+        blk = S[3 + 2 * j:5 + 2 * j, 3 + 2 * j:5 + 2 * j]
+        w = np.linalg.eigvalsh(blk)
+        assert abs(mk[j, 3] - 2 * np.sqrt(w[1] * 5.991)) < 1e-6 * mk[j, 3] and abs(mk[j, 4] - 2 * np.sqrt(w[0] * 5.991)) < 1e-6 * mk[j, 3]
+        R = np.array([[np.cos(mk[j, 2]), -np.sin(mk[j, 2])], [np.sin(mk[j, 2]), np.cos(mk[j, 2])]])
+        lam = (mk[j, 3:5] / 2) ** 2 / 5.991
+        assert rel_fro(R @ np.diag(lam) @ R.T, blk) < 1e-5
 
 
 def test_gps_pose_rows(engine_lib):
