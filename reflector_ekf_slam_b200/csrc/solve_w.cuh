@@ -93,27 +93,41 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     const bool live = c < n;
     const int cl = min(c, ld - 1);
     const double p0 = Sg[cl], p1 = Sg[(size_t)ld + cl], p2 = Sg[(size_t)2 * ld + cl];
-    constexpr int kIt = 14;                           // 28 Σ reads in flight per lane: two rounds at r = 200
-    for (int qb = warp; qb < r32; qb += 8 * kIt) {
+    // The two measurement rows of one reflector (rows 2k, 2k+1: :272-275) read the same two rows of Σ, so the gather
+    // walks row PAIRS: 28 Σ reads in flight per lane cover r = 224 in a single latency round (the L1 left beside two
+    // 111 KB CTAs is a few KB: a repeated read is another trip to L2).
+    constexpr int kIt = 14;
+    for (int pb = warp; 2 * pb < r32; pb += 8 * kIt) {
       double va[kIt], vb[kIt];
 #pragma unroll
       for (int it = 0; it < kIt; ++it) {
-        const int q = qb + 8 * it;
+        const int q = 2 * (pb + 8 * it);
         const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
         va[it] = (slot >= 0) ? Sg[(size_t)slot * ld + cl] : 0.0;
         vb[it] = (slot >= 0) ? Sg[(size_t)(slot + 1) * ld + cl] : 0.0;
       }
 #pragma unroll
       for (int it = 0; it < kIt; ++it) {
-        const int q = qb + 8 * it;
-        if (q < r32) {
-          double y = 0.0;
-          if (q < r && live) {
-            const double *h = sh + 6 * q;
-            y = h[0] * p0 + h[1] * p1 + h[2] * p2;
-            if (h[5] >= 0.0) y += h[3] * va[it] + h[4] * vb[it];
+        const int q0 = 2 * (pb + 8 * it);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int q = q0 + e;
+          if (q < r32) {
+            double y = 0.0;
+            if (q < r && live) {
+              const double *h = sh + 6 * q;
+              y = h[0] * p0 + h[1] * p1 + h[2] * p2;
+              const int slot = (int)h[5];
+              if (slot >= 0) {
+                double xa = va[it], xb = vb[it];
+                if (e == 1 && slot != (int)sh[6 * q0 + 5]) {   // never the case for the reference's row layout; kept general
+                  xa = Sg[(size_t)slot * ld + cl]; xb = Sg[(size_t)(slot + 1) * ld + cl];
+                }
+                y += h[3] * xa + h[4] * xb;
+              }
+            }
+            Y[q * kW3YS + lane] = y;
           }
-          Y[q * kW3YS + lane] = y;
         }
       }
     }
