@@ -6,7 +6,7 @@ for every session of the batch.  Per GPU the workload is `--sessions` independen
 through the same launches (BASELINE config 5 = 64 sessions over 8 GPUs = 8 per GPU; that per-GPU slice is
 the default at every N, so scaling is weak).  `value` = sessions x steps / device time, inputs resident in
 HBM (rekf_replay_device).  `e2e` = the same metric through the host-buffer C-ABI calls
-(rekf_batch_handle_odometry / _observation + rekf_batch_get_pose every step).
+(rekf_batch_handle_step + the poses of every step read back).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--sessions S] [--impl reference]
 
@@ -314,8 +314,7 @@ def run_b200(args):
     Kb = Ke // 2
     t0 = time.perf_counter()
     for k in range(Kb):
-        batch.handle_odometry(od[k])
-        batch.handle_observation(ot[k], ox[k])
+        batch.handle_step(od[k], ot[k], ox[k])
         batch.poses(poses)
     e2e_block_s = time.perf_counter() - t0
     # (3b) streaming form: every step's poses still come back to the host, through the pinned ring, but the host
@@ -324,8 +323,7 @@ def run_b200(args):
     pending = []
     t0 = time.perf_counter()
     for k in range(Kb, Ke):
-        batch.handle_odometry(od[k])
-        batch.handle_observation(ot[k], ox[k])
+        batch.handle_step(od[k], ot[k], ox[k])
         pending.append(batch.request_poses())
         if len(pending) > LAG:
             batch.fetch_poses(pending.pop(0), poses)
@@ -340,7 +338,7 @@ def run_b200(args):
     e2e_value = world * S * Ke_stream / e2e_s
     h2d = S * (4 * 8) + S * (8 + 4 * 8 + 4) + S * M_OBS * 8
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": S * 24, "steps": Ke_stream,
-           "api": "rekf_batch_handle_odometry + rekf_batch_handle_observation + rekf_batch_request_poses per step (host buffers in, "
+           "api": "rekf_batch_handle_step (odometry + observation message of every session, host buffers) + rekf_batch_request_poses per step ("
                   f"poses of every step out through the pinned ring, ticket redeemed {LAG} steps later)",
            "blocking": {"value": world * S * Kb / e2e_block_s, "steps": Kb,
                         "api": "same calls with rekf_batch_get_pose (host waits for the pose) after every step"}}

@@ -135,6 +135,12 @@ REKF_API int rekf_batch_handle_odometry(rekf_handle *h, const double *odom);
 REKF_API int rekf_batch_handle_observation(rekf_handle *h, const double *times, const float *xy,
                                            const int *counts, int m_stride);
 
+/* One whole step per session in one call: HandleOdometryMessage(odom[s]) followed by HandleObservationMessage(times[s],
+ * xy[s]) — the message pair SURVEY.md §8(d) defines as a step.  Same results as the two calls above; the pair travels
+ * in one host-to-device copy and, with use_graphs, runs as one CUDA graph per pipeline group. */
+REKF_API int rekf_batch_handle_step(rekf_handle *h, const double *odom, const double *times, const float *xy,
+                                    const int *counts, int m_stride);
+
 /* Whole-sequence replay from DEVICE-resident streams (no host traffic inside): for t in [0,T):
  * HandleOdometryMessage(odom[s][t]) then HandleObservationMessage(obs_time[s][t], obs_xy[s][t]).
  * d_odom: S x T x 4 doubles; d_obs_time: S x T doubles; d_obs_xy: S x T x m x 2 floats;

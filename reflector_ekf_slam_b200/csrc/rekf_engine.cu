@@ -53,10 +53,14 @@ struct Group {
   int slot = 0;
   InputRef host_in{};
   // replay graph (one step of this group)
-  cudaGraphExec_t step_graph = nullptr;     // whole step, or its latency-bound half when the groups are staggered
-  cudaGraphExec_t wide_graph = nullptr;     // staggered groups: the bandwidth-bound half (TRSM, SYRK, augmentation)
-  InputRef graph_in{};
-  int64_t step_launches = 0;   // kernel nodes in the captured step graph(s)
+  // one step (odometry + observation message) as CUDA graph(s): for the device-resident replay and for the host-message
+  // step call (the mailbox is at a fixed address, so that chain is static too)
+  struct StepGraphs {
+    cudaGraphExec_t step = nullptr;          // whole step, or its latency-bound half when the groups are staggered
+    cudaGraphExec_t wide = nullptr;          // staggered groups: the bandwidth-bound half (TRSM, SYRK, augmentation)
+    InputRef in{};
+    int64_t launches = 0;                    // kernel nodes per step
+  } replay_gs, host_gs;
   cudaEvent_t done = nullptr;  // join marker
   cudaEvent_t phase_ev = nullptr;   // recorded when this group's latency-bound half of a step has been issued
   bool phase_recorded = false;
@@ -294,6 +298,45 @@ int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
   return rc;
 }
 
+// (re)capture the fused step chain of one group for the inputs `in` (k_observation_front takes the odometry message,
+// k_augment advances the replay counter)
+int capture_step(rekf_handle *h, Group &g, const InputRef &in, Group::StepGraphs &gs) {
+  if (gs.step && std::memcmp(&in, &gs.in, sizeof(InputRef)) == 0 && (gs.wide != nullptr) == staggered(h, g)) return 0;
+  if (gs.step) { cudaGraphExecDestroy(gs.step); gs.step = nullptr; }
+  if (gs.wide) { cudaGraphExecDestroy(gs.wide); gs.wide = nullptr; }
+  const bool split = staggered(h, g);          // two graphs, so that the stagger events sit between them
+  const int64_t before = h->launches;
+  for (int part = 0; part < (split ? 2 : 1); ++part) {
+    cudaGraph_t cg = nullptr;
+    CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    if (part == 0) rc = launch_obs_narrow(h, g, in);
+    if (!rc && (part == 1 || !split)) rc = launch_obs_wide(h, g, in);
+    cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    CK(cudaGraphInstantiate(part == 0 ? &gs.step : &gs.wide, cg, 0));
+    cudaGraphDestroy(cg);
+  }
+  gs.in = in;
+  gs.launches = h->launches - before;          // kernel nodes per step
+  h->launches = before;                        // the capture pass itself launched nothing
+  return 0;
+}
+
+int launch_step(rekf_handle *h, Group &g, Group::StepGraphs &gs) {
+  int rc = h->stagger_mode == 1 ? stagger_wait(h, g) : 0;
+  if (rc) return rc;
+  CK(cudaGraphLaunch(gs.step, g.stream));
+  if (gs.wide) {
+    if ((rc = h->stagger_mode == 1 ? stagger_mark(h, g) : stagger_wait(h, g))) return rc;
+    CK(cudaGraphLaunch(gs.wide, g.stream));
+    if (h->stagger_mode != 1 && (rc = stagger_mark(h, g))) return rc;
+  }
+  h->launches += gs.launches;
+  return 0;
+}
+
 int stage_reserve(rekf_handle *h, size_t elems) {
   if (elems <= h->stage_elems) return 0;
   if (h->stage_dev) cudaFree(h->stage_dev);
@@ -369,8 +412,10 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
 }
 
 void destroy_group(Group &g) {
-  if (g.step_graph) cudaGraphExecDestroy(g.step_graph);
-  if (g.wide_graph) cudaGraphExecDestroy(g.wide_graph);
+  for (Group::StepGraphs *gs : {&g.replay_gs, &g.host_gs}) {
+    if (gs->step) cudaGraphExecDestroy(gs->step);
+    if (gs->wide) cudaGraphExecDestroy(gs->wide);
+  }
   if (g.phase_ev) cudaEventDestroy(g.phase_ev);
   if (g.mb_host) cudaFreeHost(g.mb_host);
   if (g.pose_host) cudaFreeHost(g.pose_host);
@@ -600,7 +645,7 @@ int rekf_handle_odometry(rekf_handle *h, double time, double vx, double vy, doub
 }
 
 static int observation_common(rekf_handle *h, const double *times, const float *xy, const int *counts,
-                              int m_stride, const double *gps /*S x 4 or null*/) {
+                              int m_stride, const double *gps /*S x 4 or null*/, const double *odom = nullptr /*S x 4: fused step*/) {
   const Layout &L = h->L;
   CK(cudaSetDevice(h->device));
   for (int s = 0; s < L.S; ++s) {
@@ -621,11 +666,25 @@ static int observation_common(rekf_handle *h, const double *times, const float *
       cnt[q] = m;
       if (m > 0) std::memcpy(dst + (size_t)q * L.mcap * 2, xy + (size_t)(grp.s0 + q) * m_stride * 2, sizeof(float) * 2 * m);
     }
-    // one copy: time | gps | count | xy (only as far as the last session's data reaches)
+    // one copy: [odom |] time | gps | count | xy (only as far as the last session's data reaches)
     const size_t end = grp.off_xy + ((size_t)(grp.Sg - 1) * L.mcap + (size_t)counts[grp.s0 + grp.Sg - 1]) * 2 * sizeof(float);
-    CK(cudaMemcpyAsync(grp.mb_dev + grp.off_time, slot + grp.off_time, end - grp.off_time, cudaMemcpyHostToDevice, grp.stream));
+    const size_t begin = odom ? grp.off_odom : grp.off_time;
+    if (odom) std::memcpy(slot + grp.off_odom, odom + (size_t)grp.s0 * 4, sizeof(double) * 4 * grp.Sg);
+    CK(cudaMemcpyAsync(grp.mb_dev + begin, slot + begin, end - begin, cudaMemcpyHostToDevice, grp.stream));
     CK(cudaEventRecord(grp.slot_done[grp.slot], grp.stream));
-    int rc = launch_observation(h, grp, grp.host_in);
+    int rc = 0;
+    if (odom) {                                        // both messages of the step: the fused chain, as a graph if allowed
+      InputRef in = grp.host_in;
+      in.fuse_odom = 1;
+      static const bool host_graphs = std::getenv("REKF_HOST_GRAPHS") ? std::atoi(std::getenv("REKF_HOST_GRAPHS")) != 0 : false;   // measured: direct launches win on the host path
+      if (host_graphs && h->opts.use_graphs && !h->profiling) {
+        if (!(rc = capture_step(h, grp, in, grp.host_gs))) rc = launch_step(h, grp, grp.host_gs);
+      } else {
+        rc = launch_observation(h, grp, in);
+      }
+    } else {
+      rc = launch_observation(h, grp, grp.host_in);
+    }
     if (rc) return rc;
   }
   return REKF_OK;
@@ -634,6 +693,12 @@ static int observation_common(rekf_handle *h, const double *times, const float *
 int rekf_batch_handle_observation(rekf_handle *h, const double *times, const float *xy, const int *counts, int m_stride) {
   if (!h || !times || !counts || (!xy && m_stride > 0)) return REKF_ERR_BAD_ARGUMENT;
   return observation_common(h, times, xy, counts, m_stride, nullptr);
+}
+
+int rekf_batch_handle_step(rekf_handle *h, const double *odom, const double *times, const float *xy, const int *counts, int m_stride) {
+  if (!h || !odom || !times || !counts || (!xy && m_stride > 0)) return REKF_ERR_BAD_ARGUMENT;
+  if (h->opts.use_imu) return observation_common(h, times, xy, counts, m_stride, nullptr);   // :213-222: odometry ignored
+  return observation_common(h, times, xy, counts, m_stride, nullptr, odom);
 }
 
 int rekf_handle_observation(rekf_handle *h, double time, const float *xy, int m, const double *gps_pose_or_null) {
@@ -674,43 +739,16 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     in.pose_ss = (long long)T * 3;
     CK(cudaMemsetAsync(g.L.step, 0, sizeof(int), g.stream));
     if (!graphs) continue;
-    const bool same = g.step_graph && std::memcmp(&in, &g.graph_in, sizeof(InputRef)) == 0;
-    if (!same) {
-      if (g.step_graph) { cudaGraphExecDestroy(g.step_graph); g.step_graph = nullptr; }
-      if (g.wide_graph) { cudaGraphExecDestroy(g.wide_graph); g.wide_graph = nullptr; }
-      const bool split = staggered(h, g);        // two graphs, so that the stagger events sit between them
-      const int64_t before = h->launches;
-      for (int part = 0; part < (split ? 2 : 1); ++part) {
-        cudaGraph_t cg = nullptr;
-        CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
-        int rc = 0;
-        if (part == 0) rc = launch_obs_narrow(h, g, in);      // k_observation_front takes the odometry message too
-        if (!rc && (part == 1 || !split)) rc = launch_obs_wide(h, g, in);   // k_augment advances the step counter
-        cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
-        if (rc) return rc;
-        if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-        CK(cudaGraphInstantiate(part == 0 ? &g.step_graph : &g.wide_graph, cg, 0));
-        cudaGraphDestroy(cg);
-      }
-      g.graph_in = in;
-      g.step_launches = h->launches - before;    // kernel nodes per step
-      h->launches = before;                      // the capture pass itself launched nothing
-    }
+    int rc = capture_step(h, g, in, g.replay_gs);
+    if (rc) return rc;
   }
   // groups are issued round-robin; each one's stream orders its own steps, nothing orders groups against each other
   for (int t = 0; t < T; ++t) {
     for (size_t gi = 0; gi < act.size(); ++gi) {
       Group &g = *act[gi];
       if (graphs) {
-        int rc = h->stagger_mode == 1 ? stagger_wait(h, g) : 0;
+        int rc = launch_step(h, g, g.replay_gs);
         if (rc) return rc;
-        CK(cudaGraphLaunch(g.step_graph, g.stream));
-        if (g.wide_graph) {
-          if ((rc = h->stagger_mode == 1 ? stagger_mark(h, g) : stagger_wait(h, g))) return rc;
-          CK(cudaGraphLaunch(g.wide_graph, g.stream));
-          if (h->stagger_mode != 1 && (rc = stagger_mark(h, g))) return rc;
-        }
-        h->launches += g.step_launches;
         continue;
       }
       int rc = launch_observation(h, g, ins[gi]);

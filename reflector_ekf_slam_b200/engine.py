@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "rekf_predict_state", "rekf_set_state", "rekf_set_map", "rekf_get_map", "rekf_load_map_txt", "rekf_save_map_txt",
     "rekf_sync", "rekf_stream", "rekf_timer_start", "rekf_timer_stop", "rekf_profile_enable", "rekf_profile_read",
     "rekf_launch_count", "rekf_device_error_flags", "rekf_debug_copy", "rekf_batch_request_poses", "rekf_batch_fetch_poses",
-    "rekf_get_markers",
+    "rekf_get_markers", "rekf_batch_handle_step",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library(path=None):
         "rekf_batch_request_poses": (i, [vp, P(C.c_int64)]),
         "rekf_batch_fetch_poses": (i, [vp, C.c_int64, vp]),
         "rekf_get_markers": (i, [vp, i, vp, i, P(i)]),
+        "rekf_batch_handle_step": (i, [vp, vp, vp, vp, vp, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -149,6 +150,15 @@ class EKFBatch:
         times = np.ascontiguousarray(times, np.float64).reshape(self.S)
         counts = np.full(self.S, m, np.int32) if counts is None else np.ascontiguousarray(counts, np.int32).reshape(self.S)
         self._ck(self.lib.rekf_batch_handle_observation(self.h, _ptr(times), _ptr(xy), _ptr(counts), m))
+
+    def handle_step(self, odom, times, xy, counts=None):
+        """One whole step per session: the odometry message (S, 4) then the observation message — one call, one copy."""
+        odom = np.ascontiguousarray(odom, np.float64).reshape(self.S, 4)
+        xy = np.ascontiguousarray(xy, np.float32).reshape(self.S, -1, 2)
+        m = xy.shape[1]
+        times = np.ascontiguousarray(times, np.float64).reshape(self.S)
+        counts = np.full(self.S, m, np.int32) if counts is None else np.ascontiguousarray(counts, np.int32).reshape(self.S)
+        self._ck(self.lib.rekf_batch_handle_step(self.h, _ptr(odom), _ptr(times), _ptr(xy), _ptr(counts), m))
 
     def replay_device(self, d_odom, d_obs_time, d_obs_xy, T, m, d_pose_out=None):
         """Device pointers (ints): odom S x T x 4 f64, obs_time S x T f64, obs_xy S x T x m x 2 f32."""

@@ -339,6 +339,13 @@ def test_pipeline_groups_bitwise(engine_lib, groups):
         e.replay_device(d_odom.data_ptr(), d_time.data_ptr(), d_xy.data_ptr(), T, m, d_pose.data_ptr())
         e.sync()
         poses.append(d_pose.cpu().numpy())
+    # the one-call step (both messages, one copy, one graph per group) == the two message calls
+    stepper = EKFBatch(S, pipeline_groups=groups, use_graphs=1, **kw)
+    for k in range(nb + 2 * T):
+        stepper.handle_step(np.stack([st["odom"][k] for st in sts]), np.array([st["obs_time"][k] for st in sts]),
+                            np.stack([st["obs_xy"][k] for st in sts]), np.array([st["obs_count"][k] for st in sts]))
+    for s in range(S):
+        assert np.array_equal(stepper.mu(s), ref.mu(s)) and np.array_equal(stepper.sigma(s), ref.sigma(s))
     for e, p in zip(engines[1:], poses[1:]):
         assert np.array_equal(p, poses[0])
         for s in range(S):
