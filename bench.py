@@ -187,7 +187,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -380,7 +380,7 @@ def run_b200(args):
         }
         if single:
             out["single_session"] = single
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     batch.close()
     if world > 1:
         dist.destroy_process_group()

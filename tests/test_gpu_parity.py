@@ -115,6 +115,34 @@ def test_c4_omni_full_size(engine_lib, cov):
     print(f"C4/{cov}: final |dmu| {d[0]:.2e} m, rel-Fro {d[1]:.2e}")
 
 
+def test_c3_long_run_drift_i8(engine_lib):
+    """Config C3, default int8-slice tensor-core covariance update, 80 steady steps: the error against the fp64 oracle
+    must stay inside the north-star bar over the RUN (a per-step bias would integrate), the covariance must stay
+    exactly symmetric, its trace must have shrunk, and the association lists must agree every step."""
+    from oracle.pyoracle import STRUCTURED, Oracle
+    from reflector_ekf_slam_b200.engine import ReflectorEKFSLAM
+    from reflector_ekf_slam_b200.synth import make_stream
+    st = make_stream("C3", 80)
+    orc = Oracle(algebra=STRUCTURED)
+    for k in range(st["n_build"]):
+        drive_oracle(orc, st, k)
+    t, mu, sig = orc.GetState()
+    ekf = ReflectorEKFSLAM(max_landmarks=1024, max_observations=100, cov_update=COV_MODES["i8"])
+    ekf.set_state(t, st["odom"][st["n_build"] - 1][1:4], mu, sig)
+    worst = (0.0, 0.0)
+    for k in range(st["n_build"], len(st["odom"])):
+        drive_engine(ekf, st, k)
+        drive_oracle(orc, st, k)
+        compare_matches(ekf, orc, f"C3 step {k}")
+        if (k - st["n_build"]) % 20 == 19:
+            d = compare_state(ekf, orc, tag=f"C3/i8 long run step {k}")
+            worst = (max(worst[0], d[0]), max(worst[1], d[1]))
+    S = ekf.GetCoviarance()
+    assert np.array_equal(S, S.T) and ekf.error_flags() == 0
+    assert np.trace(S) < np.trace(sig)                    # 80 updates of 100 landmarks each remove far more than the odometry noise adds
+    print(f"C3/i8 80 steps: worst |dmu| {worst[0]:.2e} m, worst rel-Fro {worst[1]:.2e}")
+
+
 def test_covariance_stays_exactly_symmetric_and_psd(engine_lib):
     from reflector_ekf_slam_b200.synth import make_stream
     st = make_stream("T1", 20)
