@@ -281,20 +281,21 @@ def run_b200(args):
     syrk_us = prof[syrk_name][0]
     n_ref, r = 3 + 2 * N_LM, 2 * M_OBS
     hbm_peak, bf16_peak, peak_kind = measured_peaks()
-    alg_bytes = syrk_algorithmic_bytes(n_ref, r) * S
+    Sl = -(-S // G)                                    # sessions per launch: every kernel is launched once per pipeline group
+    alg_bytes = syrk_algorithmic_bytes(n_ref, r) * Sl
     achieved = alg_bytes / (syrk_us * 1e-6) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "syrk_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(f"S{S}")
+            traffic = json.load(open(tp)).get(f"S{Sl}")
         except Exception:
             traffic = None
-    flops_useful = 2.0 * n_ref * n_ref * r * S
+    flops_useful = 2.0 * n_ref * n_ref * r * Sl
     roofline = {
         "kernel": syrk_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": traffic,
-        "algorithmic_bytes_per_launch": alg_bytes, "kernel_us": syrk_us, "share_of_step": syrk_us / step_us,
+        "algorithmic_bytes_per_launch": alg_bytes, "sessions_per_launch": Sl, "kernel_us": syrk_us, "share_of_step": syrk_us / step_us,
         "tensor": {"useful_tflops": flops_useful / (syrk_us * 1e-6) / 1e12, "executed_tflops": 0.75 * flops_useful / (syrk_us * 1e-6) / 1e12,
                    "tf32_peak_tflops": bf16_peak / 2, "note": "tf32 peak taken as half the measured bf16 peak; executed = 3 tf32 products over the upper triangle only"},
         "kernels_us": {k: round(v[0], 2) for k, v in prof.items()},

@@ -41,7 +41,8 @@ struct ProfRecord { int id; cudaEvent_t a, b; };
 // stream) is the only group when pipeline_groups <= 1 and the one used while per-kernel profiling is on.
 struct Group {
   int s0 = 0, Sg = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;       // where this group's work is issued (the handle's main stream while profiling)
+  cudaStream_t home_stream = nullptr;  // the group's own stream
   bool own_stream = false;
   Layout L{};
   // device mailbox for host-delivered messages of this group's sessions + pinned staging ring
@@ -172,10 +173,11 @@ struct ProfScope {
   }
 };
 
-// the groups that carry the hot path right now: per-kernel profiling wants one kernel on the GPU at a time
+// the groups that carry the hot path.  Per-kernel profiling wants one kernel on the GPU at a time and the SAME launch
+// shapes as the timed path: rekf_profile_enable re-homes every group onto the handle's main stream meanwhile.
 inline std::vector<Group *> active_groups(rekf_handle *h) {
   std::vector<Group *> v;
-  if (h->groups.empty() || h->profiling) v.push_back(&h->whole);
+  if (h->groups.empty()) v.push_back(&h->whole);
   else for (auto &g : h->groups) v.push_back(&g);
   return v;
 }
@@ -183,7 +185,7 @@ inline std::vector<Group *> active_groups(rekf_handle *h) {
 // host-blocking join of every stream of the handle (cold paths: getters, setters, mode switches)
 inline cudaError_t join_all(rekf_handle *h) {
   for (auto &g : h->groups) {
-    cudaError_t e = cudaStreamSynchronize(g.stream);
+    cudaError_t e = cudaStreamSynchronize(g.home_stream);
     if (e != cudaSuccess) return e;
   }
   return cudaStreamSynchronize(h->stream);
@@ -368,6 +370,7 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   g.s0 = s0;
   g.Sg = Sg;
   g.stream = stream;
+  g.home_stream = stream;
   g.own_stream = own_stream;
   g.L = h->L;
   g.L.s0 = s0;
@@ -422,7 +425,7 @@ void destroy_group(Group &g) {
   for (auto &e : g.slot_done) if (e) cudaEventDestroy(e);
   for (auto &e : g.pose_done) if (e) cudaEventDestroy(e);
   if (g.done) cudaEventDestroy(g.done);
-  if (g.own_stream && g.stream) cudaStreamDestroy(g.stream);
+  if (g.own_stream && g.home_stream) cudaStreamDestroy(g.home_stream);
 }
 
 // ---- landmark map text format ---------------------------------------------------------------
@@ -1126,6 +1129,7 @@ int rekf_profile_enable(rekf_handle *h, int enable) {
   CK(join_all(h));
   drain_profile(h);
   h->profiling = enable != 0;
+  for (auto &g : h->groups) g.stream = h->profiling ? h->stream : g.home_stream;
   if (enable) {
     std::memset(h->prof_us, 0, sizeof(h->prof_us));
     std::memset(h->prof_calls, 0, sizeof(h->prof_calls));

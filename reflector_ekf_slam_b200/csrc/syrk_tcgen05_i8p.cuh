@@ -91,6 +91,12 @@ __global__ void __launch_bounds__(kPThreads, 1)
 k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_sig) {
   timeline_mark(L, 6);
+#ifdef REKF_SYRK_TIMING
+  // per-CTA stamps (thread 0 = an epilogue thread): start, after setup, first tile done, last tile done, exit, tiles
+  auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (double)t; };
+  double *tlog = L.innov + (size_t)blockIdx.x * 6;
+  if (threadIdx.x == 0) { tlog[0] = gtime(); tlog[2] = 0; tlog[3] = 0; tlog[5] = 0; }
+#endif
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *ops = base;                                   // [4][24 KB] int8 slice boxes
@@ -136,13 +142,28 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   bool timeout = false;
+#ifdef REKF_SYRK_TIMING
+  if (threadIdx.x == 0) tlog[1] = gtime();
+#endif
 
   // item → (session, tile); false = nothing to do for it (the fetcher skips those, the other roles never see them)
   auto decode = [&](int item, int &s, int &i0, int &j0, int &r, int &n, bool &inA) -> bool {
-    const int sl = item / tiles;
+    // queue order: every session's diagonal tiles first (direct global-memory epilogue: the slow ones), then the
+    // off-diagonal tiles — the tail of the launch then consists of uniform, fast tiles
+    const int ndiag = Tn64 * L.Sg;                       // two diagonal 128x64 tiles per 128-row block
+    int sl, rem, ti = 0;
+    if (item < ndiag) {
+      sl = item / Tn64;
+      const int d = item - sl * Tn64;
+      ti = d >> 1; rem = d & 1;
+    } else {
+      const int noff = tiles - Tn64, it2 = item - ndiag;
+      sl = it2 / noff;
+      rem = it2 - sl * noff;
+      while (rem >= Tn64 - 2 * ti - 2) { rem -= Tn64 - 2 * ti - 2; ++ti; }
+      rem += 2;
+    }
     s = L.s0 + sl;
-    int rem = item - sl * tiles, ti = 0;
-    while (rem >= Tn64 - 2 * ti) { rem -= Tn64 - 2 * ti; ++ti; }
     const int tj = 2 * ti + rem;
     i0 = ti * 128; j0 = tj * kI8TileN;
     inA = rem < 2;
@@ -423,12 +444,18 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[set]);                      // this thread is done with the accumulator set
+#ifdef REKF_SYRK_TIMING
+      if (threadIdx.x == 0) { const double t = gtime(); if (iter == 0) tlog[2] = t; tlog[3] = t; tlog[5] += 1; }
+#endif
       ++iter;
       if (!inA) ++sit;
     }
   }
   if (timeout) atomicOr(&L.st[L.s0].flags, FLAG_TCGEN05_TIMEOUT);
   __syncthreads();
+#ifdef REKF_SYRK_TIMING
+  if (threadIdx.x == 0) tlog[4] = gtime();
+#endif
   if (warp == kPEpiWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
