@@ -17,11 +17,10 @@
 // Ten int8 MMAs of K=32 replace three tf32 MMAs of K=8, so the tensor time per tile is unchanged.
 // (kind::i8 exists on sm_100a; B300/sm_103a dropped it.)
 //
-// Operands: Wq[session][p][c][k] int8, K-major, 64-byte swizzle; TMA boxes of 128 (A) / 64 (B) rows x 64 k.
-// CTA = one 128x64 tile on or above the diagonal: warp 8 TMA producer (2-stage ring), warp 9 MMA issuer
-// (M=128, N=64, four 64-column s32 accumulators = 256 TMEM columns), warps 0-7 epilogue (tcgen05.ld → fp64 →
-// Σ[i][j] and the mirrored Σ[j][i]).  96 KB of shared memory and 256 TMEM columns per CTA, so two CTAs
-// share an SM and one's epilogue (HBM-bound) overlaps the other's TMA + MMA phase.
+// This header holds the scheme's shared pieces (slice constants, the kind::i8 MMA and descriptor helpers, 256-bit global
+// accesses); the kernel itself is the persistent k_syrk_tcgen05_i8p in syrk_tcgen05_i8p.cuh (the first, one-tile-per-CTA
+// form of it was retired when the persistent one overtook it).
+// Operands: Wq[session][slice][k/64][c][64] int8, K-major, 64-byte swizzle; TMA boxes of 128 (A) / 64 (B) rows x 64 k.
 #pragma once
 #include "syrk_tcgen05.cuh"
 

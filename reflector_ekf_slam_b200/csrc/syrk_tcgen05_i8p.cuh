@@ -12,8 +12,9 @@
 //     (coalesced across lanes);
 //   * the s32 accumulators are double-buffered in TMEM (2 x 4 x 64 columns = all 512), so the tensor pipe works on
 //     tile t+1 while the epilogue warps drain tile t;
-//   * warp roles: 0-7 epilogue, 8 operand TMA producer (2-stage ring of int8 slice boxes), 9 MMA issuer
-//     (tcgen05.mma.kind::i8), 10 Σ-tile TMA loader.
+//   * warp roles: 0-15 epilogue, 16 operand TMA producer (2-stage ring; one 5-D box per operand per stage: 4 digit
+//     slices x rows x 64 K-bytes, contiguous in the chunk-tiled Wq layout), 17 MMA issuer (tcgen05.mma.kind::i8),
+//     18 Σ-tile TMA loader + column scales/flags, 19 Σ-tile TMA store.
 // Tiles that touch the diagonal (34 of 306 at C3) keep the direct global-memory epilogue: their lower triangle is
 // written as mirror elements by the same CTA, which a whole-box TMA store would race with.
 #pragma once
@@ -27,30 +28,16 @@ constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ:
 constexpr int kPSigSlots = 4;                            // Σ half-tile ring: two whole tiles, so loads run a full tile ahead
 constexpr int kPMaxSess = 32;                           // sessions whose (r, n) are cached in shared memory
 constexpr int kPQ = 4;                                   // work-item ring entries
-// Operand ring: K = 32 per stage (one MMA k-step, 32-byte swizzle), FOUR stages.  The kernel was operand-latency bound
-// with two 64-K stages (ncu: the epilogue warps' top stall was the wait for acc_full): only one 48 KB load could be in
-// flight while the other stage was consumed; now three 24 KB loads are.
-#ifndef REKF_SYRK_KBOX
-#define REKF_SYRK_KBOX 64
-#endif
-constexpr int kPKBox = REKF_SYRK_KBOX;                   // 32 (32-byte swizzle, 4 stages) or 64 (64-byte swizzle, 2 stages)
-constexpr int kPBoxA = 128 * kPKBox;                     // 4 KB
-constexpr int kPBoxB = kI8TileN * kPKBox;                // 2 KB
-constexpr int kPStageBytes = kI8Slices * (kPBoxA + kPBoxB);   // 24 KB
+// Operand ring: K = 64 per stage (two MMA k-steps, 64-byte swizzle), two stages.  A 4-stage ring of 32-K boxes (32-byte
+// swizzle) was tried when the epilogue's top stall was the wait for acc_full: no gain — the kernel is bound by L2 sector
+// throughput (operand re-reads), not by operand latency.
+constexpr int kPKBox = 64;
+constexpr int kPBoxA = 128 * kPKBox;                     // 8 KB
+constexpr int kPBoxB = kI8TileN * kPKBox;                // 4 KB
+constexpr int kPStageBytes = kI8Slices * (kPBoxA + kPBoxB);   // 48 KB
 constexpr int kPStages = 128 / kPKBox;
 // operand ring + Σ ring + alignment slack + barriers + [2][64] column scales + [2][64] column flags + session table
 constexpr int kPSmemBytes = kPStages * kPStageBytes + kPSigSlots * kPSigHalf + 1024 + 512 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8 + 64;
-// K-major, SWIZZLE_32B: rows of 32 bytes, 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(256 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)6 << 61;                               // SWIZZLE_32B
-  return d;
-}
-
 struct SyrkI8P {
   CUtensorMap map_a, map_b, map_sig;
   int num_sms = 148;
@@ -76,9 +63,7 @@ __device__ __forceinline__ bool mbar_wait_backoff(uint64_t *bar, uint32_t parity
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return true;
-#ifndef REKF_SYRK_NOSLEEP
     __nanosleep(64);
-#endif
   }
   return false;
 }
@@ -99,7 +84,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
 #endif
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *ops = base;                                   // [4][24 KB] int8 slice boxes
+  uint8_t *ops = base;                                   // [2][48 KB] int8 slice boxes
   uint8_t *sig = base + kPStages * kPStageBytes;         // [4][32 KB] Σ half-tiles
   uint64_t *bars = reinterpret_cast<uint64_t *>(sig + kPSigSlots * kPSigHalf);
   uint64_t *op_full = bars, *op_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10, *sig_full = bars + 12,
@@ -244,8 +229,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
               for (int p = 0; p <= sgrp; ++p) {
                 const int q = sgrp - p;
                 const uint32_t aa = sa + p * kPBoxA + koff, bb = sb + q * bstride + koff;
-                tc_mma_i8(acc + sgrp * kI8TileN, kPKBox == 32 ? make_kmajor_sw32_desc(aa) : make_kmajor_sw64_desc(aa),
-                          kPKBox == 32 ? make_kmajor_sw32_desc(bb) : make_kmajor_sw64_desc(bb), kIdescI8, (first && p == 0) ? 0u : 1u);
+                tc_mma_i8(acc + sgrp * kI8TileN, make_kmajor_sw64_desc(aa), make_kmajor_sw64_desc(bb), kIdescI8, (first && p == 0) ? 0u : 1u);
               }
             }
           }
@@ -478,10 +462,10 @@ inline const char *syrk_i8p_init(SyrkI8P &tc, const Layout &L) {
   const cuuint32_t box_a[5] = {64u, 128u, 1u, (cuuint32_t)kI8Slices, 1u};
   const cuuint32_t box_b[5] = {64u, (cuuint32_t)kI8TileN, 1u, (cuuint32_t)kI8Slices, 1u};
   if (encode(&tc.map_a, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, L.Wq, dims, strides, box_a, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             kPKBox == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return "cuTensorMapEncodeTiled(Wq, A box) failed";
   if (encode(&tc.map_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, L.Wq, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             kPKBox == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return "cuTensorMapEncodeTiled(Wq, B box) failed";
   const cuuint64_t sdims[3] = {(cuuint64_t)L.ld, (cuuint64_t)L.ld, (cuuint64_t)L.S};
   const cuuint64_t sstrides[2] = {(cuuint64_t)L.ld * sizeof(double), (cuuint64_t)L.ld * L.ld * sizeof(double)};
