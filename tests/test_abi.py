@@ -58,7 +58,8 @@ def test_product_package_does_not_import_oracle():
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions(engine_lib):
-    """UTCHMMA (tcgen05.mma), UTMALDG (TMA) and LDTM (tcgen05.ld) must be in the shipped binary."""
+    """UTCHMMA / UTCIMMA (tcgen05.mma kind::tf32 / kind::i8), UTMALDG / UTMASTG (TMA tensor loads and stores), UBLKCP
+    (cp.async.bulk: the Cholesky triangle), LDTM (tcgen05.ld) and DMMA (fp64 tensor pipe) must be in the shipped binary."""
     import shutil
     import subprocess
     exe = shutil.which("cuobjdump")
@@ -66,5 +67,5 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(engine_lib):
         pytest.skip("cuobjdump not available")
     lib = os.path.join(ROOT, "reflector_ekf_slam_b200", "librekf_b200.so")
     sass = subprocess.run([exe, "-sass", lib], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+    for mnemonic in ("UTCHMMA", "UTCIMMA", "UTMALDG.5D", "UTMASTG", "UBLKCP", "LDTM", "DMMA"):
         assert mnemonic in sass, mnemonic
