@@ -362,7 +362,7 @@ def run_b200(args):
     # ---- (5) CPU baseline (rank 0, N = 1 only): the reference's as-written algebra on the host -----------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, desc = cpu_reference(budget_s=args.cpu_budget_s, max_steps=2, threads=1)
+        v, desc = cpu_reference(budget_s=args.cpu_budget_s, max_steps=5, threads=1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc}
 
     if rank == 0:
