@@ -14,6 +14,11 @@ from reflector_ekf_slam_b200._abi import RekfOptions, make_options  # noqa: F401
 _HERE = os.path.dirname(os.path.abspath(__file__))
 AS_WRITTEN = 0
 STRUCTURED = 1
+# oracle/_ref only: instantiate ekf::ReflectorEKFSLAMGPS (reflector_ekf_slam_gps.cc) instead of ekf::ReflectorEKFSLAM
+REF_GPS_CLASS = 0x100
+
+REFERENCE_ROOT = "/root/reference"
+REF_DIR = os.path.join(_HERE, "_ref")
 
 _libs = {}
 
@@ -22,6 +27,45 @@ def build(native=False):
     """(Re)build liboracle.so (and liboracle_native.so) with the committed Makefile."""
     target = "native" if native else "all"
     subprocess.run(["make", "-s", "-C", _HERE, target], check=True)
+
+
+def build_ref():
+    """Compile the reference's own translation units into oracle/_ref/ (only where /root/reference exists:
+    this container; the GPU box uses the prebuilt files that travel with the snapshot)."""
+    if not os.path.isdir(REFERENCE_ROOT):
+        return False
+    subprocess.run(["make", "-s", "-C", _HERE, "ref"], check=True)
+    return True
+
+
+def ref_available():
+    return os.path.exists(os.path.join(REF_DIR, "librekf_ref.so")) or os.path.isdir(REFERENCE_ROOT)
+
+
+def _cpu_has_avx2_fma():
+    try:
+        flags = open("/proc/cpuinfo").read()
+    except OSError:
+        return False
+    return " avx2" in flags and " fma" in flags
+
+
+def load_ref(fast=False):
+    """oracle/_ref/librekf_ref.so: ekf::ReflectorEKFSLAM{,GPS} compiled unmodified from /root/reference
+    against oracle/shim (see ref_abi.cc), same ABI as liboracle.so.  fast=True picks the -mavx2 -mfma build
+    when the CPU has it (timing only; the reference's own CMake build is the plain -O3 one)."""
+    name = "librekf_ref_avx2.so" if (fast and _cpu_has_avx2_fma()) else "librekf_ref.so"
+    if name in _libs:
+        return _libs[name]
+    path = os.path.join(REF_DIR, name)
+    if os.path.isdir(REFERENCE_ROOT):
+        build_ref()          # make: no-op when up to date
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path}: build it with `make -C oracle ref` where /root/reference exists")
+    lib = C.CDLL(path)
+    _bind(lib, ref=True)
+    _libs[name] = lib
+    return lib
 
 
 def load(native=False):
@@ -33,6 +77,12 @@ def load(native=False):
     if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
         build(native)
     lib = C.CDLL(path)
+    _bind(lib, ref=False)
+    _libs[name] = lib
+    return lib
+
+
+def _bind(lib, ref):
     P = C.POINTER
     lib.oracle_create.restype = C.c_void_p
     lib.oracle_create.argtypes = [P(RekfOptions), C.c_int]
@@ -56,11 +106,12 @@ def load(native=False):
     lib.oracle_load_map_txt.argtypes = [C.c_void_p, C.c_char_p]
     lib.oracle_save_map_txt.argtypes = [C.c_void_p, C.c_char_p]
     lib.oracle_save_map_txt.restype = C.c_int
-    lib.oracle_dgemm.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
-    lib.oracle_lu_inverse.argtypes = [C.c_int, C.c_void_p, C.c_int]
-    lib.oracle_lu_inverse.restype = C.c_int
-    _libs[name] = lib
-    return lib
+    if ref:
+        lib.oracle_ref_track_matches.argtypes = [C.c_void_p, C.c_int]
+    else:
+        lib.oracle_dgemm.argtypes = [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        lib.oracle_lu_inverse.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        lib.oracle_lu_inverse.restype = C.c_int
 
 
 def _ptr(a):
@@ -70,8 +121,8 @@ def _ptr(a):
 class Oracle:
     """One CPU filter.  Method names follow the reference class (reflector_ekf_slam.h:20-44)."""
 
-    def __init__(self, options=None, algebra=STRUCTURED, native=False, **kw):
-        self.lib = load(native)
+    def __init__(self, options=None, algebra=STRUCTURED, native=False, lib=None, **kw):
+        self.lib = lib if lib is not None else load(native)
         self.options = options if options is not None else make_options(**kw)
         self.h = self.lib.oracle_create(C.byref(self.options), int(algebra))
         self.algebra = algebra
@@ -156,3 +207,13 @@ class Oracle:
 
     def save_map_txt(self, filebase):
         return self.lib.oracle_save_map_txt(self.h, filebase.encode())
+
+
+class Reference(Oracle):
+    """The reference's own ekf::ReflectorEKFSLAM (gps=True: ekf::ReflectorEKFSLAMGPS), compiled unmodified
+    from /root/reference into oracle/_ref/ — the pin for the restatement above and for the CUDA engine."""
+
+    def __init__(self, options=None, gps=False, fast=False, track_matches=True, **kw):
+        super().__init__(options, algebra=(REF_GPS_CLASS if gps else 0), lib=load_ref(fast), **kw)
+        if not track_matches:
+            self.lib.oracle_ref_track_matches(self.h, 0)
