@@ -9,9 +9,12 @@
 //
 // Internal state ordering (differs from the reference's [x y θ l0x l0y …] to keep every landmark
 // pair 16-byte aligned): slot 0,1,2 = x,y,θ; slot 3 = zero padding (row and column of Σ stay 0
-// under every kernel); landmark j occupies slots 4+2j, 5+2j.  Σ is stored dense, exactly symmetric,
-// fp64, row pitch `ld` (a multiple of 128 so tcgen05 tiles never straddle the buffer edge).
-// The reference ordering is restored at the C-ABI boundary (k_pack_sigma / k_pack_mu).
+// under every kernel); landmark j occupies slots 4+2j, 5+2j.  Σ is fp64 with row pitch `ld` (a multiple
+// of 128 so tcgen05 tiles never straddle the buffer edge) and ONLY ITS UPPER TRIANGLE (row <= column) IS
+// MAINTAINED: every kernel reads Σ[i][j] through sym_idx() and writes the upper element only, so the
+// covariance downdate — the HBM-bound part of the step — moves half the bytes and needs no mirrored
+// (transposed) stores; what lies below the diagonal is stale and never read.  The reference ordering and
+// the full symmetric column-major matrix are restored at the C-ABI boundary (k_pack_sigma / k_pack_mu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -64,7 +67,10 @@ struct InputRef {
   int fuse_odom;            // replay: k_observation_front handles the step's odometry message first (no k_odometry launch)
   double *pose_out;         // optional: pose after the step, pose_out + s*pose_ss + t*3
   long long pose_ss;
+  const InputRef *indirect; // non-null: the real descriptor lives at this DEVICE address (replay graphs are captured once
+                            // with only this pointer baked in; rekf_replay_device rewrites the descriptor, not the graph)
 };
+__device__ __forceinline__ InputRef resolve_input(const InputRef &in) { return in.indirect ? *in.indirect : in; }
 
 struct Layout {
   int S;          // sessions of the handle (extent of every [S]-leading array and of the TMA maps)
@@ -122,6 +128,10 @@ __device__ __forceinline__ void timeline_mark(const Layout &L, int kernel_id) {
   }
 }
 __host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }
+// offset of Σ[i][j] in the upper-triangle-only storage
+__host__ __device__ __forceinline__ size_t sym_idx(int i, int j, int ld) {
+  return i <= j ? (size_t)i * ld + j : (size_t)j * ld + i;
+}
 // byte offset of digit slice p, state slot `row`, measurement byte `kbyte` in Layout::Wq
 __host__ __device__ inline size_t wq_offset(const Layout &L, int s, int p, int row, int kbyte) {
   return ((((size_t)s * 4 + p) * (L.kq >> 6) + (kbyte >> 6)) * L.ld + row) * 64 + (kbyte & 63);

@@ -845,10 +845,13 @@ int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) 
   const Layout &L = h->L;
   CK(join_all(h));
   CK(cudaMemcpyAsync(pose, L.mu + (size_t)session * L.ld, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
-  if (cov33)   // the block is symmetric, so row- vs column-major is immaterial
+  if (cov33)
     CK(cudaMemcpy2DAsync(cov33, sizeof(double) * 3, L.sigma + (size_t)session * L.ld * L.ld, sizeof(double) * L.ld,
                          sizeof(double) * 3, 3, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
+  if (cov33)   // only the upper triangle is stored on the device (row i <= column j sits at cov33[j + 3 i] of the copy)
+    for (int i = 0; i < 3; ++i)
+      for (int j = i + 1; j < 3; ++j) cov33[i + 3 * j] = cov33[j + 3 * i];
   return REKF_OK;
 }
 

@@ -80,8 +80,9 @@ __device__ inline double wrap_angle(double a) {
 }
 
 // Σ ← G_xi·Σ·G_xiᵀ + G_u·Qu·G_uᵀ, μ[0:3] += d, θ wrapped — by one CTA, O(n).  G_xi is the identity
-// plus two entries, so only rows/columns 0 and 1 change: row 0 += g02·row 2, row 1 += g12·row 2 and
-// the mirrored columns (the two n³ products of :178/:202 reduce to this without changing a sum).
+// plus two entries, so only rows/columns 0 and 1 change: row 0 += g02·row 2, row 1 += g12·row 2 (the
+// columns are their mirror images and are not stored; the two n³ products of :178/:202 reduce to this
+// without changing a sum).
 __device__ inline void predict_cta(const Layout &L, int s, double dt) {
   SessionState &st = L.st[s];
   double *mu = L.mu + (size_t)s * L.ld;
@@ -93,18 +94,14 @@ __device__ inline void predict_cta(const Layout &L, int s, double dt) {
   const MotionTerms t = motion_model(L, vt, theta, dt);
   for (int c = kPoseSlots + threadIdx.x; c < n; c += blockDim.x) {
     const double s2 = Sg[(size_t)2 * ld + c];
-    const double v0 = Sg[c] + t.g02 * s2;
-    const double v1 = Sg[(size_t)ld + c] + t.g12 * s2;
-    Sg[c] = v0;
-    Sg[(size_t)ld + c] = v1;
-    Sg[(size_t)c * ld] = v0;
-    Sg[(size_t)c * ld + 1] = v1;
+    Sg[c] += t.g02 * s2;
+    Sg[(size_t)ld + c] += t.g12 * s2;
   }
   __syncthreads();   // everyone has read mu[2] / st before thread 0 rewrites them
   if (threadIdx.x == 0) {
     double P[9], T[9];
     for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) P[i * 3 + j] = Sg[(size_t)i * ld + j];
+      for (int j = 0; j < 3; ++j) P[i * 3 + j] = Sg[sym_idx(i, j, ld)];
     // T = G3·P (rows), P' = T·G3ᵀ (columns)
     for (int j = 0; j < 3; ++j) {
       T[0 + j] = P[0 + j] + t.g02 * P[6 + j];
@@ -117,11 +114,7 @@ __device__ inline void predict_cta(const Layout &L, int s, double dt) {
       P[i * 3 + 2] = T[i * 3 + 2];
     }
     for (int i = 0; i < 3; ++i)
-      for (int j = i; j < 3; ++j) {
-        const double v = P[i * 3 + j] + t.V[i * 3 + j];
-        Sg[(size_t)i * ld + j] = v;
-        Sg[(size_t)j * ld + i] = v;   // keep Σ exactly symmetric
-      }
+      for (int j = i; j < 3; ++j) Sg[(size_t)i * ld + j] = P[i * 3 + j] + t.V[i * 3 + j];
     mu[0] += t.d[0];
     mu[1] += t.d[1];
     mu[2] = wrap_angle(mu[2] + t.d[2]);
@@ -146,8 +139,9 @@ __device__ inline void odometry_cta(const Layout &L, int s, const InputRef &in) 
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in) {
+__global__ void __launch_bounds__(1024, 1) k_odometry(Layout L, InputRef in_arg) {
   timeline_mark(L, 0);
+  const InputRef in = resolve_input(in_arg);
   odometry_cta(L, L.s0 + blockIdx.x, in);
 }
 
@@ -165,8 +159,9 @@ __device__ inline void warp_argmin(double &d, int &j) {
 
 constexpr int kMatchNew = 0, kMatchState = 1, kMatchMap = 2;
 
-__global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in) {
+__global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in_arg) {
   timeline_mark(L, 1);
+  const InputRef in = resolve_input(in_arg);
   extern __shared__ int sm_i[];
   const int s = L.s0 + blockIdx.x;
   if (in.fuse_odom) odometry_cta(L, s, in);        // replay: this step's HandleOdometryMessage first
@@ -354,7 +349,7 @@ __global__ void __launch_bounds__(256) k_innovation(Layout L) {
   double acc = 0;
   for (int b = 0; b < nb; ++b) {       // ((H·Σ)·Hᵀ): y_b = Σ_a H[q,a]·Σ[a,b]
     double y = 0;
-    for (int a = 0; a < na; ++a) y += ha[a] * Sg[(size_t)ia[a] * ld + ib[b]];
+    for (int a = 0; a < na; ++a) y += ha[a] * Sg[sym_idx(ia[a], ib[b], ld)];
     acc += y * hb[b];
   }
   if (p == q) acc += L.Qd[(size_t)s * L.rcap + q];
@@ -536,16 +531,12 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
   for (int cc = warp; cc < kWCols; cc += 8) {
     const int c = c0 + cc;
     if (c < n) {
-      const double *rowc = Sg + (size_t)c * ld;
-      const double p0 = rowc[0], p1 = rowc[1], p2 = rowc[2];
+      const double p0 = Sg[sym_idx(0, c, ld)], p1 = Sg[sym_idx(1, c, ld)], p2 = Sg[sym_idx(2, c, ld)];
       for (int q = lane; q < r; q += 32) {
         const double *h = Hp + 4 * q;
         double y = h[0] * p0 + h[1] * p1 + h[2] * p2;
         const int slot = Hslot[q];
-        if (slot >= 0) {
-          const double2 v = *reinterpret_cast<const double2 *>(rowc + slot);
-          y += Hl[2 * q] * v.x + Hl[2 * q + 1] * v.y;
-        }
+        if (slot >= 0) y += Hl[2 * q] * Sg[sym_idx(slot, c, ld)] + Hl[2 * q + 1] * Sg[sym_idx(slot + 1, c, ld)];
         Y[q * kYS + cc] = y;
       }
     } else {
@@ -692,7 +683,7 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Σ −= Wᵀ·W on the fp64 pipe: 64x64 upper-triangular tiles, mirrored (exact symmetry by construction)
+// Σ −= Wᵀ·W on the fp64 pipe: 64x64 tiles on/above the diagonal, upper elements only
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
   timeline_mark(L, 5);
@@ -746,9 +737,7 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
     for (int v = 0; v < 4; ++v) {
       const int i = i0 + ty * 4 + u, j = j0 + tx * 4 + v;
       if (i < n && j < n && i <= j) {
-        const double val = Sg[(size_t)i * ld + j] - acc[u][v];
-        Sg[(size_t)i * ld + j] = val;
-        Sg[(size_t)j * ld + i] = val;
+        Sg[(size_t)i * ld + j] -= acc[u][v];
       }
     }
   __syncthreads();
@@ -758,8 +747,9 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
 // ---------------------------------------------------------------------------------------------
 // augmentation (:311-364) + end-of-step bookkeeping
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
+__global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in_arg) {
   timeline_mark(L, 7);
+  const InputRef in = resolve_input(in_arg);
   const int s = L.s0 + blockIdx.z;
   SessionState &st = L.st[s];
   const int t_idx = current_step(in);
@@ -780,18 +770,15 @@ __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
     // cross blocks: Σ[new rows][c] = G_p·Σ[0:3][c]  (:355-357), c over the old state
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < n) {
-      const double s0 = Sg[c], s1 = Sg[(size_t)ld + c], s2 = Sg[(size_t)2 * ld + c];
+      const double s0 = Sg[c], s1 = Sg[sym_idx(1, c, ld)], s2 = Sg[sym_idx(2, c, ld)];
       for (int q = 0; q < N2; ++q) {
         const int i = nw[q];
         const double rx = (double)xy[2 * i], ry = (double)xy[2 * i + 1];   // :344-345
         const double g0 = -rx * sn - ry * cs, g1 = rx * cs - ry * sn;       // :347
         const double v0 = s0 + g0 * s2;     // [1 0 g0]·Σ[0:3][c]
         const double v1 = s1 + g1 * s2;     // [0 1 g1]·Σ[0:3][c]
-        const int slot = n + 2 * q;
-        Sg[(size_t)slot * ld + c] = v0;
-        Sg[(size_t)(slot + 1) * ld + c] = v1;
-        Sg[(size_t)c * ld + slot] = v0;
-        Sg[(size_t)c * ld + slot + 1] = v1;
+        const int slot = n + 2 * q;               // c < n <= slot: the upper-triangle element is (c, slot)
+        *reinterpret_cast<double2 *>(Sg + (size_t)c * ld + slot) = make_double2(v0, v1);
       }
     }
     if (blockIdx.x == 0) {
@@ -799,14 +786,14 @@ __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
       // 2x2 block — off-diagonal ones too — receives R(θ)·Qt·R(θ)ᵀ (reference quirk kept)
       double P[9];
       for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) P[a * 3 + b] = Sg[(size_t)a * ld + b];
+        for (int b = 0; b < 3; ++b) P[a * 3 + b] = Sg[sym_idx(a, b, ld)];
       const double qo = L.q_obs;
       const double GQG[4] = {(cs * qo) * cs + (-sn * qo) * (-sn), (cs * qo) * sn + (-sn * qo) * cs,
                              (sn * qo) * cs + (cs * qo) * (-sn), (sn * qo) * sn + (cs * qo) * cs};
       const int R = 2 * N2;
       for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
         const int i = e / R, j = e - i * R;
-        if (i > j) continue;                       // upper + mirror keeps Σ exactly symmetric
+        if (i > j) continue;                       // upper triangle only
         const int oi = nw[i >> 1], oj = nw[j >> 1];
         const double rxi = (double)xy[2 * oi], ryi = (double)xy[2 * oi + 1];
         const double rxj = (double)xy[2 * oj], ryj = (double)xy[2 * oj + 1];
@@ -821,7 +808,6 @@ __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in) {
         }
         const double v = acc + GQG[(i & 1) * 2 + (j & 1)];
         Sg[(size_t)(n + i) * ld + n + j] = v;
-        Sg[(size_t)(n + j) * ld + n + i] = v;
       }
       // new means, rounded through float32 (:327-331, :341-342)
       for (int q = threadIdx.x; q < N2; q += blockDim.x) {
@@ -868,7 +854,7 @@ __global__ void k_pack_sigma(Layout L, int s, double *out, int ld_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
   if (i >= n_ref || j >= n_ref) return;
   const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
-  out[(size_t)j * ld_out + i] = Sg[(size_t)ref_to_slot(j) * L.ld + ref_to_slot(i)];
+  out[(size_t)j * ld_out + i] = Sg[sym_idx(ref_to_slot(i), ref_to_slot(j), L.ld)];
 }
 __global__ void k_pack_mu(Layout L, int s, double *out) {
   const int n_ref = 3 + 2 * L.st[s].N;
@@ -884,7 +870,7 @@ __global__ void k_pack_landmarks(Layout L, int s, double *xy, double *cov) {
   const double *mu = L.mu + (size_t)s * L.ld;
   xy[2 * j] = mu[a]; xy[2 * j + 1] = mu[a + 1];
   cov[4 * j + 0] = Sg[(size_t)a * L.ld + a];       cov[4 * j + 1] = Sg[(size_t)a * L.ld + a + 1];
-  cov[4 * j + 2] = Sg[(size_t)(a + 1) * L.ld + a]; cov[4 * j + 3] = Sg[(size_t)(a + 1) * L.ld + a + 1];
+  cov[4 * j + 2] = Sg[(size_t)a * L.ld + a + 1]; cov[4 * j + 3] = Sg[(size_t)(a + 1) * L.ld + a + 1];
 }
 // Node::ReflectorToRosMarkers (ros_node.cc:736-789) on the device: per landmark the mean and the 95 % covariance ellipse
 // (chi-square 5.991, :763-764) of its 2x2 block.  The reference takes the eigen-decomposition from Eigen::EigenSolver,
@@ -912,7 +898,7 @@ __global__ void k_unpack_state(Layout L, int s, const double *mu_in, const doubl
   if (i >= n_ref || j >= n_ref) return;
   double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
   const double v = 0.5 * (sig_in[(size_t)j * ld_in + i] + sig_in[(size_t)i * ld_in + j]);
-  Sg[(size_t)ref_to_slot(i) * L.ld + ref_to_slot(j)] = v;
+  if (i <= j) Sg[(size_t)ref_to_slot(i) * L.ld + ref_to_slot(j)] = v;
   if (j == 0) L.mu[(size_t)s * L.ld + ref_to_slot(i)] = mu_in[i];
 }
 // PredictState (:97-152) into a packed copy: out_mu (n_ref), out_sigma column-major or nullptr
@@ -937,10 +923,10 @@ __global__ void k_predict_state(Layout L, int s, double time, double *out_mu, do
   // (G Σ Gᵀ)[i][j] = Σ_ab G[i][a] Σ[a][b] G[j][b], G = I + g02·e0e2ᵀ + g12·e1e2ᵀ
   const double gi = i == 0 ? t.g02 : (i == 1 ? t.g12 : 0.0);
   const double gj = j == 0 ? t.g02 : (j == 1 ? t.g12 : 0.0);
-  double v = Sg[(size_t)a * ld + b];
-  if (i < 2) v += gi * Sg[(size_t)2 * ld + b];
+  double v = Sg[sym_idx(a, b, ld)];
+  if (i < 2) v += gi * Sg[sym_idx(2, b, ld)];
   if (j < 2) {
-    double col2 = Sg[(size_t)a * ld + 2];
+    double col2 = Sg[sym_idx(a, 2, ld)];
     if (i < 2) col2 += gi * Sg[(size_t)2 * ld + 2];
     v += gj * col2;
   }

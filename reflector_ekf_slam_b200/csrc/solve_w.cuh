@@ -85,14 +85,25 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     }
     __syncthreads();
     REKF_WSTAMP2();
-    // lane = column (its Σ row and pose entries stay in registers), warps stride the measurement rows: the row
-    // descriptor is one broadcast read, the Y store is conflict free, eight Σ reads are in flight per lane
-    // Σ is bit-exactly symmetric, so Σ[b][c] is read as row b, columns c0..c0+31: every access of the gather is a
-    // coalesced 256-byte segment (reading row c at scattered slots would cost one 32-byte sector per element)
+    // lane = column (its pose entries stay in registers), warps stride the measurement rows: the row descriptor is one
+    // broadcast read, the Y store is conflict free, 28 Σ reads are in flight per lane.
+    // Only the upper triangle of Σ is stored.  Σ[slot][c] with slot < c is row `slot`, columns c0..c0+31: a coalesced
+    // 256-byte segment per warp.  Slots to the right of this CTA's columns (slot > c) are read as Σ[c][slot..slot+1]:
+    // ONE 16-byte read per lane covers both rows of the reflector (a full 32-byte sector for 16 useful bytes — the price
+    // of never writing the lower triangle, paid on ~half of 3.4 MB per session-step).
     const int c = c0 + lane;
     const bool live = c < n;
     const int cl = min(c, ld - 1);
-    const double p0 = Sg[cl], p1 = Sg[(size_t)ld + cl], p2 = Sg[(size_t)2 * ld + cl];
+    const double p0 = Sg[sym_idx(0, cl, ld)], p1 = Sg[sym_idx(1, cl, ld)], p2 = Sg[sym_idx(2, cl, ld)];
+    auto sig_pair = [&](int slot, double &xa, double &xb) {     // Σ[slot][c], Σ[slot+1][c]; slot is even, >= 4
+      if (slot > cl) {
+        const double2 v = *reinterpret_cast<const double2 *>(Sg + (size_t)cl * ld + slot);
+        xa = v.x; xb = v.y;
+      } else {
+        xa = Sg[(size_t)slot * ld + cl];
+        xb = Sg[sym_idx(slot + 1, cl, ld)];
+      }
+    };
     // The two measurement rows of one reflector (rows 2k, 2k+1: :272-275) read the same two rows of Σ, so the gather
     // walks row PAIRS: 28 Σ reads in flight per lane cover r = 224 in a single latency round (the L1 left beside two
     // 111 KB CTAs is a few KB: a repeated read is another trip to L2).
@@ -103,8 +114,8 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       for (int it = 0; it < kIt; ++it) {
         const int q = 2 * (pb + 8 * it);
         const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
-        va[it] = (slot >= 0) ? Sg[(size_t)slot * ld + cl] : 0.0;
-        vb[it] = (slot >= 0) ? Sg[(size_t)(slot + 1) * ld + cl] : 0.0;
+        va[it] = vb[it] = 0.0;
+        if (slot >= 0) sig_pair(slot, va[it], vb[it]);
       }
 #pragma unroll
       for (int it = 0; it < kIt; ++it) {
@@ -120,9 +131,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
               const int slot = (int)h[5];
               if (slot >= 0) {
                 double xa = va[it], xb = vb[it];
-                if (e == 1 && slot != (int)sh[6 * q0 + 5]) {   // never the case for the reference's row layout; kept general
-                  xa = Sg[(size_t)slot * ld + cl]; xb = Sg[(size_t)(slot + 1) * ld + cl];
-                }
+                if (e == 1 && slot != (int)sh[6 * q0 + 5]) sig_pair(slot, xa, xb);   // never the case for the reference's row layout; kept general
                 y += h[3] * xa + h[4] * xb;
               }
             }

@@ -4,7 +4,7 @@
 // (a landmark seen again after a long time, the pose after dead reckoning) that is not small against the
 // posterior, so k_solve_w3 flags such slots (Wflag / exact_list) and the tensor kernel skips every element
 // whose row or column is flagged.  This kernel computes exactly those elements in fp64 from the fp64 panel
-// W64: Σ[a][j] −= Σ_k W[k][a]·W[k][j] for every flagged slot a and every column j, mirrored to Σ[j][a].
+// W64: Σ[a][j] −= Σ_k W[k][a]·W[k][j] for every flagged slot a and every column j (stored once, in the upper triangle).
 // A pair of flagged slots (a, a') is owned by the smaller index so that it is subtracted once.
 // One warp per element (lanes stride k, shuffle reduction): a handful of flagged slots per frame cost ~n·r
 // FMAs each — microseconds — where routing the whole frame to the fp64 SYRK would cost a millisecond.
@@ -37,11 +37,7 @@ __device__ __forceinline__ void syrk_exact_rows(const Layout &L, int s) {
       for (int k = lane; k < r; k += 32) acc = fma(wa[k], wj[k], acc);
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-      if (lane == 0) {
-        const double v = Sg[(size_t)a * ld + j] - acc;
-        Sg[(size_t)a * ld + j] = v;
-        Sg[(size_t)j * ld + a] = v;
-      }
+      if (lane == 0) Sg[sym_idx(a, j, ld)] -= acc;
     }
   }
 }

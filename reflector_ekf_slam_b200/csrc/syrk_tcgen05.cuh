@@ -13,8 +13,8 @@
 //             K-block into a 3-stage shared-memory ring, mbarrier complete_tx signalling
 //   warp 9  : MMA issuer   — one elected thread issues tcgen05.mma.cta_group::1.kind::tf32
 //             (M=128, N=128, K=8), tcgen05.commit releases ring slots and finally publishes the accumulators
-//   warps 0-7: epilogue    — tcgen05.ld 32x32b.x16, Σ[i][j] ← Σ[i][j] − (main+corr) in fp64, and the same
-//             value to Σ[j][i]: the mirror write makes Σ symmetric bit for bit and halves the MMA work.
+//   warps 0-7: epilogue    — tcgen05.ld 32x32b.x16, Σ[i][j] ← Σ[i][j] − (main+corr) in fp64, upper triangle only
+//             (the lower triangle is not stored, rekf_device.cuh).
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -232,16 +232,11 @@ k_syrk_tcgen05(Layout L, const __grid_constant__ CUtensorMap map_hi, const __gri
         if (!diag && jbase + 15 < n) {
 #pragma unroll
           for (int u = 0; u < 16; u += 2) *reinterpret_cast<double2 *>(row + u) = make_double2(cur[u], cur[u + 1]);
-#pragma unroll
-          for (int u = 0; u < 16; ++u) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
         } else {
 #pragma unroll
           for (int u = 0; u < 16; ++u) {
             const int j = jbase + u;
-            if (j < n && (!diag || i <= j)) {
-              row[u] = cur[u];
-              if (i != j) Sg[(size_t)j * ld + i] = cur[u];
-            }
+            if (j < n && (!diag || i <= j)) row[u] = cur[u];
           }
         }
       }

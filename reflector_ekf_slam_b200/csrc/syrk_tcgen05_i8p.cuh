@@ -1,22 +1,25 @@
 // syrk_tcgen05_i8p.cuh — persistent, fully overlapped form of the exact int8-slice covariance SYRK
-// (Σ −= Wᵀ·W, reflector_ekf_slam.cc:308; arithmetic identical to syrk_tcgen05_i8.cuh — see there for the
-// digit-slice scheme).  What changes is the data movement, because the kernel is HBM-bound:
+// (Σ −= Wᵀ·W, reflector_ekf_slam.cc:308; see syrk_tcgen05_i8.cuh for the digit-slice scheme).  The kernel is bound by
+// data movement, so the design is about bytes:
 //
-//   * one CTA per SM pulls (session, tile) work items — 128x64 tiles on/above the diagonal — from a device-wide
-//     atomic queue (the operand producer fetches one item ahead and publishes it to the other roles through a
-//     4-entry shared-memory ring), so a CTA that starts late — its SM was still running another pipeline group's
-//     Cholesky — simply takes fewer tiles instead of stretching the launch;
-//   * Σ tiles travel by TMA in both directions: 128-row x 32-column half-tiles (2 boxes of 16 columns, 128-byte
-//     swizzle) in a four-slot shared-memory ring (two whole tiles) — full-line HBM reads issued a whole tile ahead, full-line
-//     writes, no partial sectors, no L1 thrash; only the mirrored lower-triangle copy is written from registers
-//     (coalesced across lanes);
+//   * only the UPPER triangle of Σ exists (rekf_device.cuh): 128x64 tiles on/above the diagonal, no mirrored stores;
+//   * the SM never READS Σ.  The epilogue turns the s32 accumulators into the fp64 downdate −G·2^(e_i+e_j) (an exact
+//     product: G is an integer below 2^51, the scales are powers of two), writes it into a shared-memory half-tile and
+//     the store warp hands it to the TMA as cp.reduce.async.bulk.tensor .add.f64: the read-modify-write of Σ happens in
+//     the L2 (one correctly rounded fp64 add per element — the same bits as an FMA on the SM, since the product is
+//     exact).  There is no HBM load latency on the SM's critical path and no load ring; measured alone
+//     (scripts/probe_tma_reduce.cu) 148 CTAs reduce-add the upper triangles of 4 C3 sessions in 26 µs, the same as an
+//     ideal TMA load + store pipeline with nothing else in the loop;
+//   * one CTA per SM pulls (session, tile) work items from a device-wide atomic queue (the operand producer fetches
+//     one item ahead and publishes it to the other roles through a 4-entry shared-memory ring), so a CTA that starts
+//     late — its SM was still running another pipeline group's Cholesky — simply takes fewer tiles;
 //   * the s32 accumulators are double-buffered in TMEM (2 x 4 x 64 columns = all 512), so the tensor pipe works on
 //     tile t+1 while the epilogue warps drain tile t;
-//   * warp roles: 0-15 epilogue, 16 operand TMA producer (2-stage ring; one 5-D box per operand per stage: 4 digit
-//     slices x rows x 64 K-bytes, contiguous in the chunk-tiled Wq layout), 17 MMA issuer (tcgen05.mma.kind::i8),
-//     18 Σ-tile TMA loader + column scales/flags, 19 Σ-tile TMA store.
-// Tiles that touch the diagonal (34 of 306 at C3) keep the direct global-memory epilogue: their lower triangle is
-// written as mirror elements by the same CTA, which a whole-box TMA store would race with.
+//   * warp roles: 0-15 epilogue, 16 operand TMA producer (one 5-D box per operand per stage: 4 digit slices x rows x
+//     64 K-bytes, contiguous in the chunk-tiled Wq layout), 17 MMA issuer (tcgen05.mma.kind::i8), 18 column
+//     scales/flags of the tile, 19 Σ reduce-add issuer.
+// Tiles that touch the diagonal (34 of 306 at C3) keep a direct global-memory epilogue: element predicates (i <= j) and
+// the exact fp64 diagonal from k_solve_w3.
 #pragma once
 #include "syrk_tcgen05_i8.cuh"
 
@@ -25,7 +28,7 @@ namespace rekf {
 constexpr int kPEpiWarps = 16;                           // epilogue warps: warp w owns TMEM lanes 32·(w%4).. and 8 of each half-tile's 32 columns
 constexpr int kPThreads = (kPEpiWarps + 4) * 32;         // + operand TMA, MMA, Σ load, Σ store
 constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ: 128 rows x 32 columns fp64 = 32 KB
-constexpr int kPSigSlots = 4;                            // Σ half-tile ring: two whole tiles, so loads run a full tile ahead
+constexpr int kPSigSlots = 4;                            // downdate half-tile ring (two whole tiles) between the epilogue and the TMA reduce
 constexpr int kPMaxSess = 32;                           // sessions whose (r, n) are cached in shared memory
 constexpr int kPQ = 4;                                   // work-item ring entries
 // Operand ring: K = 64 per stage (two MMA k-steps, 64-byte swizzle), two stages.  A 4-stage ring of 32-K boxes (32-byte
@@ -45,8 +48,9 @@ struct SyrkI8P {
   bool ready = false;
 };
 
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+// Σ[box] += smem tile, performed by the L2 (SASS: UTMAREDG.3D.ADD); the element type (fp64) comes from the tensor map
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap *map, const void *src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -85,9 +89,9 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t *ops = base;                                   // [2][48 KB] int8 slice boxes
-  uint8_t *sig = base + kPStages * kPStageBytes;         // [4][32 KB] Σ half-tiles
+  uint8_t *sig = base + kPStages * kPStageBytes;         // [4][32 KB] downdate half-tiles on their way to the TMA reduce
   uint64_t *bars = reinterpret_cast<uint64_t *>(sig + kPSigSlots * kPSigHalf);
-  uint64_t *op_full = bars, *op_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10, *sig_full = bars + 12,
+  uint64_t *op_full = bars, *op_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10,
            *sig_empty = bars + 16, *sig_done = bars + 20;
   uint64_t *sc_full = bars + 24;
   uint64_t *q_full = bars + 26, *q_empty = bars + 30;                                      // work-item ring
@@ -111,9 +115,9 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   if (warp == kPEpiWarps) {
     if (lane == 0) {
       for (int i = 0; i < kPStages; ++i) { mbar_init(&op_full[i], 1); mbar_init(&op_empty[i], 1); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPEpiWarps * 32); mbar_init(&sc_full[i], 1); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPEpiWarps * 32); mbar_init(&sc_full[i], 32); }
       for (int i = 0; i < kPSigSlots; ++i) {
-        mbar_init(&sig_full[i], 1); mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], kPEpiWarps * 32);
+        mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], kPEpiWarps * 32);
       }
       for (int i = 0; i < kPQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], kPEpiWarps + 3); }   // consumer warps
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -240,16 +244,16 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       }
     }
   } else if (warp == kPEpiWarps + 2) {
-    // ===== column scales / flags of every tile → shared memory (whole warp); Σ-tile TMA loads (lane 0, tiles strictly
-    //       above the diagonal).  The scale slot is the accumulator set's: free once the epilogue released that set. =====
-    uint32_t sit = 0, iter = 0;
+    // ===== column scales / flags of every tile → shared memory (whole warp).  The slot is the accumulator set's: free
+    //       once the epilogue released that set.  Every lane arrives for its own two entries. =====
+    uint32_t iter = 0;
     for (uint32_t q = 0; !timeout; ++q) {
       const int item = next_item(q, true);
       if (item < 0) break;
       int s, i0, j0, r, n; bool inA;
       decode(item, s, i0, j0, r, n, inA);
       const int set = iter & 1;
-      if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
+      if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) timeout = true;
       {
         const size_t off = (size_t)s * L.ld + j0 + 2 * lane;
         const double2 v = *reinterpret_cast<const double2 *>(L.Wscale + off);
@@ -257,47 +261,45 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         *reinterpret_cast<double2 *>(sc_tab + set * 64 + 2 * lane) = v;
         *reinterpret_cast<unsigned short *>(fl_tab + set * 64 + 2 * lane) = f;
       }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&sc_full[set]);
-        if (!inA) {
-          for (int h = 0; h < 2; ++h) {
-            const int slot = ((sit & 1) << 1) | h;
-            if (!mbar_wait_backoff(&sig_empty[slot], ((sit >> 1) & 1) ^ 1)) { timeout = true; break; }
-            uint8_t *dst = sig + (size_t)slot * kPSigHalf;
-            mbar_expect_tx(&sig_full[slot], kPSigHalf);
-            tma_load_3d(dst, &map_sig, &sig_full[slot], j0 + 32 * h, i0, s);
-            tma_load_3d(dst + kPSigHalf / 2, &map_sig, &sig_full[slot], j0 + 32 * h + 16, i0, s);
-          }
-        }
-      }
-      timeout = __shfl_sync(0xffffffffu, (int)timeout, 0) != 0;
+      mbar_arrive(&sc_full[set]);
+      timeout = __any_sync(0xffffffffu, timeout);
       ++iter;
-      if (!inA) ++sit;
     }
   } else if (warp == kPEpiWarps + 3) {
-    // ===== Σ-tile TMA store: waits until the 256 epilogue threads have rewritten a half-tile, stores it, frees it =====
+    // ===== Σ reduce-add issuer: waits until the 512 epilogue threads have written a downdate half-tile, hands it to the
+    //       TMA (the L2 adds it into Σ), and frees the slot one group later, when the TMA has read it out =====
     if (lane == 0) {
       uint32_t sit = 0;
+      int pending = -1;                                    // slot whose reduce has been issued but not yet released
       for (uint32_t q = 0; !timeout; ++q) {
         const int item = next_item(q, false);
         if (item < 0) break;
         int s, i0, j0, r, n; bool inA;
         decode(item, s, i0, j0, r, n, inA);
-        if (inA) continue;
+        if (inA) {
+          if (pending >= 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_arrive(&sig_empty[pending]);
+            pending = -1;
+          }
+          continue;
+        }
         for (int h = 0; h < 2; ++h) {
           const int slot = ((sit & 1) << 1) | h;
           if (!mbar_wait_backoff(&sig_done[slot], (sit >> 1) & 1)) { timeout = true; break; }
           const uint8_t *src = sig + (size_t)slot * kPSigHalf;
-          tma_store_3d(&map_sig, src, j0 + 32 * h, i0, s);
-          tma_store_3d(&map_sig, src + kPSigHalf / 2, j0 + 32 * h + 16, i0, s);
+          tma_reduce_add_3d(&map_sig, src, j0 + 32 * h, i0, s);
+          tma_reduce_add_3d(&map_sig, src + kPSigHalf / 2, j0 + 32 * h + 16, i0, s);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          mbar_arrive(&sig_empty[slot]);
+          if (pending >= 0) {
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every group but the one just issued
+            mbar_arrive(&sig_empty[pending]);
+          }
+          pending = slot;
         }
         ++sit;
       }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all Σ stores landed
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all reductions performed
     }
   } else if (warp < kPEpiWarps) {
     // ===== epilogue: warp w owns TMEM lanes 32·(w%4).. ; within a 32-column half-tile, columns 8·(w/4).. .  Sixteen warps
@@ -351,47 +353,32 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
         const double2 *scj = reinterpret_cast<const double2 *>(sct + col0);
         double cur[8];
         if (!inA) {
-          // ---- Σ half-tile staged by TMA: read own row (swizzled 16-byte chunks), update, write back, TMA store ----
+          // ---- downdate half-tile: −G·2^(e_i+e_j) (exact) into the swizzled staging slot; the TMA reduce adds it into Σ ----
           const int slot = ((sit & 1) << 1) | h;
-          if (!mbar_wait(&sig_full[slot], (sit >> 1) & 1)) timeout = true;
+          if (!mbar_wait(&sig_empty[slot], ((sit >> 1) & 1) ^ 1)) timeout = true;   // the previous reduce has read it out
           uint8_t *rowp = sig + (size_t)slot * kPSigHalf + (size_t)(cgp >> 1) * (kPSigHalf / 2) + (size_t)il * 128;
           const int ch0 = 4 * (cgp & 1);                  // this thread's four 16-byte chunks of the 128-byte row
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const double2 t = *reinterpret_cast<const double2 *>(rowp + (((ch0 + c) ^ (il & 7)) << 4));
-            cur[2 * c] = t.x; cur[2 * c + 1] = t.y;
-          }
           const bool no_flags = row_ok && (cf.x | cf.y) == 0u;   // the common case, warp-uniform but for row_ok
           if (no_flags) {
 #pragma unroll
             for (int u = 0; u < 8; u += 2) {
               const double2 sj = scj[u >> 1];
-              cur[u] = fma(-i64_to_f64(G[u]), si * sj.x, cur[u]);
-              cur[u + 1] = fma(-i64_to_f64(G[u + 1]), si * sj.y, cur[u + 1]);
+              cur[u] = -i64_to_f64(G[u]) * (si * sj.x);
+              cur[u + 1] = -i64_to_f64(G[u + 1]) * (si * sj.y);
             }
-          } else if (row_ok) {
+          } else {
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const unsigned cfw = (u < 4) ? cf.x : cf.y;
-              if (!((cfw >> (8 * (u & 3))) & 0xffu)) cur[u] = fma(-i64_to_f64(G[u]), si * sct[col0 + u], cur[u]);
+              const bool skip = !row_ok || ((cfw >> (8 * (u & 3))) & 0xffu);   // flagged slots: k_syrk_exact_rows did them
+              cur[u] = skip ? 0.0 : -i64_to_f64(G[u]) * (si * sct[col0 + u]);
             }
           }
 #pragma unroll
           for (int c = 0; c < 4; ++c)
             *reinterpret_cast<double2 *>(rowp + (((ch0 + c) ^ (il & 7)) << 4)) = make_double2(cur[2 * c], cur[2 * c + 1]);
-          // mirrored lower-triangle copy straight from registers (lanes = consecutive rows: coalesced)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&sig_done[slot]);                     // hand the half-tile to the store warp
-          if (no_flags && i < n && jbase + 7 < n) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
-          } else if (row_ok && i < n) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const unsigned cfw = (u < 4) ? cf.x : cf.y;
-              if (jbase + u < n && !((cfw >> (8 * (u & 3))) & 0xffu)) Sg[(size_t)(jbase + u) * ld + i] = cur[u];
-            }
-          }
+          mbar_arrive(&sig_done[slot]);                     // hand the half-tile to the reduce issuer
         } else {
           // ---- diagonal tile: direct global accesses, element predicates (i <= j), exact diagonal ----
           const bool want = row_ok && i < n && jbase < n && !(jbase + 7 < i);
@@ -418,10 +405,7 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
             for (int u = 0; u < 8; ++u) {
               const int j = jbase + u;
               const unsigned cfw = (u < 4) ? cf.x : cf.y;
-              if (j < n && i <= j && !((cfw >> (8 * (u & 3))) & 0xffu)) {
-                row[u] = cur[u];
-                if (i != j) Sg[(size_t)j * ld + i] = cur[u];
-              }
+              if (j < n && i <= j && !((cfw >> (8 * (u & 3))) & 0xffu)) row[u] = cur[u];
             }
           }
         }

@@ -58,7 +58,8 @@ def test_product_package_does_not_import_oracle():
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions(engine_lib):
-    """UTCHMMA / UTCIMMA (tcgen05.mma kind::tf32 / kind::i8), UTMALDG / UTMASTG (TMA tensor loads and stores), UBLKCP
+    """UTCHMMA / UTCIMMA (tcgen05.mma kind::tf32 / kind::i8), UTMALDG / UTMAREDG.3D.ADD (TMA tensor loads; the covariance
+    downdate leaves the SM as a TMA reduce-add, so there is no plain tensor store), UBLKCP
     (cp.async.bulk: the Cholesky triangle), LDTM (tcgen05.ld) and DMMA (fp64 tensor pipe) must be in the shipped binary."""
     import shutil
     import subprocess
@@ -67,5 +68,5 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(engine_lib):
         pytest.skip("cuobjdump not available")
     lib = os.path.join(ROOT, "reflector_ekf_slam_b200", "librekf_b200.so")
     sass = subprocess.run([exe, "-sass", lib], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "UTCIMMA", "UTMALDG.5D", "UTMASTG", "UBLKCP", "LDTM", "DMMA"):
+    for mnemonic in ("UTCHMMA", "UTCIMMA", "UTMALDG.5D", "UTMAREDG.3D.ADD", "UBLKCP", "LDTM", "DMMA"):
         assert mnemonic in sass, mnemonic
