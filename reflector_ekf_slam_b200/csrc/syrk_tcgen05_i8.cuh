@@ -65,7 +65,10 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;                               // SWIZZLE_64B
   return d;
 }
-// D = s32, A = B = signed int8, K-major, N = 64, M = 128
-constexpr uint32_t kIdescI8 = (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)kI8TileN >> 3) << 17) | ((128u >> 4) << 24);
+// D = s32, A = B = signed int8, K-major, M = 128, N = n (a multiple of 16 up to 256)
+__host__ __device__ constexpr uint32_t idesc_i8(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | (((uint32_t)n >> 3) << 17) | ((128u >> 4) << 24);
+}
+constexpr uint32_t kIdescI8 = idesc_i8(kI8TileN);
 
 }  // namespace rekf

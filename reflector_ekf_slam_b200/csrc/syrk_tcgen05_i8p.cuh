@@ -10,41 +10,54 @@
 //     exact).  There is no HBM load latency on the SM's critical path and no load ring; measured alone
 //     (scripts/probe_tma_reduce.cu) 148 CTAs reduce-add the upper triangles of 4 C3 sessions in 26 µs, the same as an
 //     ideal TMA load + store pipeline with nothing else in the loop;
-//   * one CTA per SM pulls (session, tile) work items from a device-wide atomic queue (the operand producer fetches
-//     one item ahead and publishes it to the other roles through a 4-entry shared-memory ring), so a CTA that starts
-//     late — its SM was still running another pipeline group's Cholesky — simply takes fewer tiles;
+//   * operand reuse: work is handed out as STRIPS — up to kPMaxStrip consecutive 128x64 tiles of one 128-row block.
+//     The row block's A panel (4 digit slices x 128 rows x K <= 256 bytes = 128 KB) is loaded once per strip and stays
+//     resident in shared memory; only the 64-row B boxes (16 KB per 64 K-bytes, 4-stage ring) stream per tile.  Per
+//     tile the SM pulls 64 KB (+128 KB / strip length) of int8 panels from L2 instead of 192 KB — the round-1 kernel
+//     was bound by exactly that L2→SM stream.  (K > 256 bytes, config C4: the panel does not fit; both operands stream
+//     through a 2-stage ring as before — template parameter kRes.)
+//   * one CTA per SM pulls strips from a device-wide atomic cursor over the linearised tile order with guided
+//     self-scheduling (strip length = remaining / (2 x CTAs), clamped to [1, kPMaxStrip]): long strips while there is
+//     plenty of work, single tiles at the end, so the launch has no tail; a CTA that starts late — its SM was still
+//     running another pipeline group's Cholesky — simply takes fewer.  The operand producer fetches one span ahead and
+//     publishes tiles to the other roles through a 4-entry shared-memory ring;
 //   * the s32 accumulators are double-buffered in TMEM (2 x 4 x 64 columns = all 512), so the tensor pipe works on
 //     tile t+1 while the epilogue warps drain tile t;
-//   * warp roles: 0-15 epilogue, 16 operand TMA producer (one 5-D box per operand per stage: 4 digit slices x rows x
-//     64 K-bytes, contiguous in the chunk-tiled Wq layout), 17 MMA issuer (tcgen05.mma.kind::i8), 18 column
-//     scales/flags of the tile, 19 Σ reduce-add issuer.
-// Tiles that touch the diagonal (34 of 306 at C3) keep a direct global-memory epilogue: element predicates (i <= j) and
-// the exact fp64 diagonal from k_solve_w3.
+//   * warp roles: 0-15 epilogue (16 columns = one TMA box at a time, double-buffered), 16 operand TMA producer (one
+//     5-D box per operand per 64 K-bytes: 4 digit slices x rows x 64 B, contiguous in the chunk-tiled Wq layout),
+//     17 MMA issuer (tcgen05.mma.kind::i8), 18 column scales/flags of the tile, 19 Σ reduce-add issuer.
+// Tiles that touch the diagonal take the same path: elements below the diagonal add 0, the diagonal itself adds the
+// exact fp64 −Σ_k W[k][i]² from k_solve_w3 instead of the truncated digit product.
 #pragma once
 #include "syrk_tcgen05_i8.cuh"
 
 namespace rekf {
 
-constexpr int kPEpiWarps = 16;                           // epilogue warps: warp w owns TMEM lanes 32·(w%4).. and 8 of each half-tile's 32 columns
-constexpr int kPThreads = (kPEpiWarps + 4) * 32;         // + operand TMA, MMA, Σ load, Σ store
-constexpr int kPSigHalf = 128 * 32 * 8;                  // one half-tile of Σ: 128 rows x 32 columns fp64 = 32 KB
-constexpr int kPSigSlots = 4;                            // downdate half-tile ring (two whole tiles) between the epilogue and the TMA reduce
-constexpr int kPMaxSess = 32;                           // sessions whose (r, n) are cached in shared memory
-constexpr int kPQ = 4;                                   // work-item ring entries
-// Operand ring: K = 64 per stage (two MMA k-steps, 64-byte swizzle), two stages.  A 4-stage ring of 32-K boxes (32-byte
-// swizzle) was tried when the epilogue's top stall was the wait for acc_full: no gain — the kernel is bound by L2 sector
-// throughput (operand re-reads), not by operand latency.
-constexpr int kPKBox = 64;
-constexpr int kPBoxA = 128 * kPKBox;                     // 8 KB
-constexpr int kPBoxB = kI8TileN * kPKBox;                // 4 KB
-constexpr int kPStageBytes = kI8Slices * (kPBoxA + kPBoxB);   // 48 KB
-constexpr int kPStages = 128 / kPKBox;
-// operand ring + Σ ring + alignment slack + barriers + [2][64] column scales + [2][64] column flags + session table
-constexpr int kPSmemBytes = kPStages * kPStageBytes + kPSigSlots * kPSigHalf + 1024 + 512 + 2 * 64 * 8 + 2 * 64 + kPMaxSess * 8 + 64;
+constexpr int kPEpiWarps = 16;                           // epilogue warps: warp w owns TMEM lanes 32·(w%4).. and 4 of a box's 16 columns
+constexpr int kPThreads = (kPEpiWarps + 4) * 32;         // + operand TMA, MMA, scales, Σ reduce
+constexpr int kPSigBox = 128 * 16 * 8;                   // one downdate box: 128 rows x 16 columns fp64 = 16 KB (128-byte swizzle)
+constexpr int kPSigSlots = 2;                            // downdate boxes in flight between the epilogue and the TMA reduce
+constexpr int kPMaxSess = 32;                            // sessions whose (r, n) are cached in shared memory
+constexpr int kPQ = 4;                                   // tile ring entries
+constexpr int kPMaxStrip = 6;                            // longest strip (tiles sharing one resident A panel)
+constexpr int kPKBox = 64;                               // K bytes per TMA box (64-byte swizzle, two MMA k-steps)
+constexpr int kPBoxA = 128 * kPKBox;                     // 8 KB per slice
+constexpr int kPBoxB = kI8TileN * kPKBox;                // 4 KB per slice
+constexpr int kPChunkA = kI8Slices * kPBoxA;             // 32 KB: all four slices of 128 rows x 64 K-bytes
+constexpr int kPChunkB = kI8Slices * kPBoxB;             // 16 KB
+constexpr int kPResChunks = 4;                           // resident A panel: K <= 256 bytes
+constexpr int kPResBStages = 4;                          // resident mode: B ring
+constexpr int kPStrStages = 2;                           // streaming mode: (A + B) ring
+constexpr int kPTables = 2048;                           // barriers, scale/flag tables, session table, tile ring
+constexpr int kPSmemRes = kPResChunks * kPChunkA + kPResBStages * kPChunkB + kPSigSlots * kPSigBox + 1024 + kPTables;   // 227 KB exactly
+constexpr int kPSmemStr = kPStrStages * (kPChunkA + kPChunkB) + kPSigSlots * kPSigBox + 1024 + kPTables;
+static_assert(kPSmemRes <= 232448, "resident-panel SYRK exceeds the 227 KB shared-memory limit");
+
 struct SyrkI8P {
   CUtensorMap map_a, map_b, map_sig;
   int num_sms = 148;
   int reserve_sms = 0;          // SMs left to the other pipeline groups' latency-bound kernels
+  bool resident = true;         // the A panel fits (kq <= 256)
   bool ready = false;
 };
 
@@ -67,40 +80,56 @@ __device__ __forceinline__ bool mbar_wait_backoff(uint64_t *bar, uint32_t parity
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return true;
-    __nanosleep(64);
+    __nanosleep(32);
   }
   return false;
+}
+// one lane of a converged warp (elect.sync): ptxas then knows a single thread issues the tcgen05/TMA instructions inside and
+// moves their operands to uniform registers once, instead of wrapping every instruction in a per-active-thread loop
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 // exact int64 → double for |g| < 2^51 without the slow I2F.F64.S64: add to the bits of 2^52+2^51, subtract it back
 __device__ __forceinline__ double i64_to_f64(long long g) {
   return __longlong_as_double(g + 0x4338000000000000LL) - 6755399441055744.0;
 }
 
+// -DREKF_SYRK_TIMING: every role's elected thread accumulates the cycles it spends in each wait (scripts/syrk_timing.py);
+// per CTA 24 doubles in the (dead by now) S/L buffer of the launch's first session
+#ifdef REKF_SYRK_TIMING
+#define REKF_T(slot, expr) do { const long long t_ = clock64(); expr; tacc[slot] += (double)(clock64() - t_); } while (0)
+#else
+#define REKF_T(slot, expr) do { expr; } while (0)
+#endif
+
+template <bool kRes>
 __global__ void __launch_bounds__(kPThreads, 1)
 k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_sig) {
   timeline_mark(L, 6);
-#ifdef REKF_SYRK_TIMING
-  // per-CTA stamps (thread 0 = an epilogue thread): start, after setup, first tile done, last tile done, exit, tiles
-  auto gtime = []() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return (double)t; };
-  double *tlog = L.innov + (size_t)blockIdx.x * 6;
-  if (threadIdx.x == 0) { tlog[0] = gtime(); tlog[2] = 0; tlog[3] = 0; tlog[5] = 0; }
-#endif
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *base = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t *ops = base;                                   // [2][48 KB] int8 slice boxes
-  uint8_t *sig = base + kPStages * kPStageBytes;         // [4][32 KB] downdate half-tiles on their way to the TMA reduce
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sig + kPSigSlots * kPSigHalf);
-  uint64_t *op_full = bars, *op_empty = bars + 4, *acc_full = bars + 8, *acc_empty = bars + 10,
-           *sig_empty = bars + 16, *sig_done = bars + 20;
-  uint64_t *sc_full = bars + 24;
-  uint64_t *q_full = bars + 26, *q_empty = bars + 30;                                      // work-item ring
+  // resident: [4 chunks][32 KB] A panel, then [4][16 KB] B ring.  streaming: [2][48 KB] (A chunk | B chunk) ring.
+  uint8_t *opsA = base;
+  uint8_t *opsB = base + (kRes ? kPResChunks * kPChunkA : 0);
+  constexpr int kOpsBytes = kRes ? kPResChunks * kPChunkA + kPResBStages * kPChunkB : kPStrStages * (kPChunkA + kPChunkB);
+  uint8_t *sig = base + kOpsBytes;                       // [2][16 KB] downdate boxes on their way to the TMA reduce
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sig + kPSigSlots * kPSigBox);
+  uint64_t *a_full = bars, *a_empty = bars + 4, *b_full = bars + 8, *b_empty = bars + 12, *acc_full = bars + 16,
+           *acc_empty = bars + 18, *sig_empty = bars + 20, *sig_done = bars + 22, *sc_full = bars + 24, *q_full = bars + 26,
+           *q_empty = bars + 30;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 34);
   double *sc_tab = reinterpret_cast<double *>(reinterpret_cast<uint8_t *>(bars) + 512);   // [2][64] Wscale of the tile's columns
   unsigned char *fl_tab = reinterpret_cast<unsigned char *>(sc_tab + 2 * 64);             // [2][64] Wflag of the tile's columns
   int *sess_r = reinterpret_cast<int *>(fl_tab + 2 * 64);                                  // [kPMaxSess] r, 0 = nothing to do
   int *sess_n = sess_r + kPMaxSess;                                                        // [kPMaxSess] internal dimension
-  volatile int *q_item = sess_n + kPMaxSess;                                               // [kPQ] item index, -1 = no more work
+  volatile int4 *q_tile = reinterpret_cast<volatile int4 *>(sess_n + kPMaxSess);           // [kPQ] {session, i0, j0, flags}; session < 0: drained
   for (int q = threadIdx.x; q < min(L.Sg, kPMaxSess); q += kPThreads) {
     const SessionState &st = L.st[L.s0 + q];
     sess_r[q] = (st.r > 0 && !st.exact_update) ? st.r : 0;
@@ -109,16 +138,14 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tn64 = L.ld / kI8TileN;
-  const int tiles = (L.ld / 128) * (L.ld / 128 + 1);
+  const int tiles = (L.ld / 128) * (L.ld / 128 + 1);     // 128x64 tiles on/above the diagonal, per session
   const int total = tiles * L.Sg;
 
   if (warp == kPEpiWarps) {
     if (lane == 0) {
-      for (int i = 0; i < kPStages; ++i) { mbar_init(&op_full[i], 1); mbar_init(&op_empty[i], 1); }
+      for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
       for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], kPEpiWarps * 32); mbar_init(&sc_full[i], 32); }
-      for (int i = 0; i < kPSigSlots; ++i) {
-        mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], kPEpiWarps * 32);
-      }
+      for (int i = 0; i < kPSigSlots; ++i) { mbar_init(&sig_empty[i], 1); mbar_init(&sig_done[i], kPEpiWarps); }
       for (int i = 0; i < kPQ; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], kPEpiWarps + 3); }   // consumer warps
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -132,126 +159,198 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   const uint32_t tmem = *tmem_slot;
   bool timeout = false;
 #ifdef REKF_SYRK_TIMING
-  if (threadIdx.x == 0) tlog[1] = gtime();
+  double tacc[6] = {0, 0, 0, 0, 0, 0};
+  double *tlog = L.Sbuf + (size_t)L.s0 * L.rld * L.sld + (size_t)blockIdx.x * 24;
+  const long long t_begin = clock64();
 #endif
 
-  // item → (session, tile); false = nothing to do for it (the fetcher skips those, the other roles never see them)
-  auto decode = [&](int item, int &s, int &i0, int &j0, int &r, int &n, bool &inA) -> bool {
-    // queue order: every session's diagonal tiles first (direct global-memory epilogue: the slow ones), then the
-    // off-diagonal tiles — the tail of the launch then consists of uniform, fast tiles
-    const int ndiag = Tn64 * L.Sg;                       // two diagonal 128x64 tiles per 128-row block
-    int sl, rem, ti = 0;
-    if (item < ndiag) {
-      sl = item / Tn64;
-      const int d = item - sl * Tn64;
-      ti = d >> 1; rem = d & 1;
-    } else {
-      const int noff = tiles - Tn64, it2 = item - ndiag;
-      sl = it2 / noff;
-      rem = it2 - sl * noff;
-      while (rem >= Tn64 - 2 * ti - 2) { rem -= Tn64 - 2 * ti - 2; ++ti; }
-      rem += 2;
-    }
-    s = L.s0 + sl;
-    const int tj = 2 * ti + rem;
-    i0 = ti * 128; j0 = tj * kI8TileN;
-    inA = rem < 2;
-    if (sl < kPMaxSess) {
-      r = sess_r[sl]; n = sess_n[sl];
-    } else {
-      const SessionState &st = L.st[s];
-      r = (st.r > 0 && !st.exact_update) ? st.r : 0; n = internal_dim(st.N);
-    }
-    return r > 0 && j0 < n;
+  // session-local r / n (0: the session has nothing for this kernel)
+  auto sess_rn = [&](int sl, int &r, int &n) {
+    if (sl < kPMaxSess) { r = sess_r[sl]; n = sess_n[sl]; }
+    else { const SessionState &st = L.st[L.s0 + sl]; r = (st.r > 0 && !st.exact_update) ? st.r : 0; n = internal_dim(st.N); }
   };
-  // consumer side of the work-item ring: entry q of the sequence, -1 = the queue is drained
-  auto next_item = [&](uint32_t q, bool whole_warp) -> int {
+  // consumer side of the tile ring
+  auto next_tile = [&](uint32_t q, bool whole_warp, int &s, int &i0, int &j0, int &flags) -> bool {
     const int slot = q & (kPQ - 1);
-    if (!mbar_wait_backoff(&q_full[slot], (q / kPQ) & 1)) { timeout = true; return -1; }
-    const int item = q_item[slot];
+    bool ok;
+    REKF_T(0, ok = mbar_wait_backoff(&q_full[slot], (q / kPQ) & 1));
+    if (!ok) { timeout = true; return false; }
+    s = q_tile[slot].x; i0 = q_tile[slot].y; j0 = q_tile[slot].z; flags = q_tile[slot].w;
     if (whole_warp) __syncwarp();
     if (!whole_warp || lane == 0) mbar_arrive(&q_empty[slot]);
-    return item;
+    return s >= 0;
   };
 
   if (warp == kPEpiWarps) {
-    // ===== operand TMA producer =====
+    // ===== operand TMA producer + work distribution =====
     if (lane == 0) {
-      uint32_t kbc = 0;
-      int nxt = atomicAdd(L.tile_counter, 1);              // fetched one item ahead: the round trip hides behind the loads
-      for (uint32_t q = 0; !timeout; ++q) {
-        int s, i0, j0, r, n; bool inA;
-        int item = nxt;
-        while (item < total && !decode(item, s, i0, j0, r, n, inA)) item = atomicAdd(L.tile_counter, 1);
-        const int slot = q & (kPQ - 1);
-        if (!mbar_wait_backoff(&q_empty[slot], ((q / kPQ) & 1) ^ 1)) { timeout = true; break; }
-        q_item[slot] = item < total ? item : -1;
+      // guided self-scheduling over the linear tile order (session-major, row-block-major inside a session)
+      // The first span of every CTA is static (CTA b takes tiles [b·w0, (b+1)·w0): no atomic round trip before the first load);
+      // the shared cursor (zeroed by the k_syrk_f64 launch in front) counts the tiles handed out after those.
+      const int w0 = min(kPMaxStrip, max(1, total / (2 * (int)gridDim.x)));
+      const int base0 = w0 * (int)gridDim.x;
+      auto grab = [&](int &start, int &cnt) {
+        const int seen = base0 + *reinterpret_cast<volatile int *>(L.tile_counter);
+        const int rem = total - seen;
+        if (rem <= 0) { start = total; cnt = 0; return; }
+        const int want = min(kPMaxStrip, max(1, rem / (2 * (int)gridDim.x)));
+        start = base0 + atomicAdd(L.tile_counter, want);
+        cnt = start < total ? min(want, total - start) : 0;
+      };
+      uint32_t qn = 0, bcnt = 0, acnt[4] = {0u, 0u, 0u, 0u};
+      auto publish = [&](int s, int i0, int j0, int flags) -> bool {
+        const int slot = qn & (kPQ - 1);
+        bool ok;
+        REKF_T(1, ok = mbar_wait_backoff(&q_empty[slot], ((qn / kPQ) & 1) ^ 1));
+        if (!ok) { timeout = true; return false; }
+        q_tile[slot].x = s; q_tile[slot].y = i0; q_tile[slot].z = j0; q_tile[slot].w = flags;
         mbar_arrive(&q_full[slot]);
-        if (item >= total) break;
-        nxt = atomicAdd(L.tile_counter, 1);
-        const int nkb = (r + kPKBox - 1) / kPKBox;
-        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-          const int stage = kbc & (kPStages - 1);
-          if (!mbar_wait_backoff(&op_empty[stage], ((kbc / kPStages) & 1) ^ 1)) { timeout = true; break; }
-          uint8_t *sa = ops + (size_t)stage * kPStageBytes, *sb = sa + kI8Slices * kPBoxA;
-          mbar_expect_tx(&op_full[stage], kI8Slices * (kPBoxA + (inA ? 0 : kPBoxB)));
-          // one box per operand: all four digit slices ride in the box's third dimension (a single thread issues
-          // these, and eight small boxes per stage made the issue rate the bottleneck)
-          tma_load_5d(sa, &map_a, &op_full[stage], 0, i0, kb, 0, s);
-          if (!inA) tma_load_5d(sb, &map_b, &op_full[stage], 0, j0, kb, 0, s);
+        ++qn;
+        return true;
+      };
+      int start = w0 * (int)blockIdx.x, cnt = start < total ? min(w0, total - start) : 0;
+      if (cnt == 0) grab(start, cnt);
+      while (cnt > 0 && !timeout) {
+        int ts[kPMaxStrip], ti0[kPMaxStrip], tj0[kPMaxStrip], tr[kPMaxStrip], nt = 0;
+        for (int l = start; l < start + cnt; ++l) {
+          const int sl = l / tiles;
+          int t = l - sl * tiles, ib = 0;
+          while (t >= Tn64 - 2 * ib) { t -= Tn64 - 2 * ib; ++ib; }
+          int r, n;
+          sess_rn(sl, r, n);
+          const int j0 = (2 * ib + t) * kI8TileN;
+          if (r > 0 && j0 < n) { ts[nt] = L.s0 + sl; ti0[nt] = ib * 128; tj0[nt] = j0; tr[nt] = r; ++nt; }
         }
-      }
-    }
-  } else if (warp == kPEpiWarps + 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      uint32_t kbc = 0, iter = 0;
-      for (uint32_t q = 0; !timeout; ++q) {
-        const int item = next_item(q, false);
-        if (item < 0) break;
-        int s, i0, j0, r, n; bool inA;
-        decode(item, s, i0, j0, r, n, inA);
-        const int set = iter & 1;
-        if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) { timeout = true; break; }
-        tc_fence_after();
-        const uint32_t acc = tmem + set * 256;
-        const int nkb = (r + kPKBox - 1) / kPKBox;
-        for (int kb = 0; kb < nkb; ++kb, ++kbc) {
-          const int stage = kbc & (kPStages - 1);
-          if (!mbar_wait_backoff(&op_full[stage], (kbc / kPStages) & 1)) { timeout = true; break; }
-          tc_fence_after();
-          const uint32_t sa = smem_u32(ops + (size_t)stage * kPStageBytes);
-          const uint32_t sb = inA ? sa + (uint32_t)(j0 - i0) * kPKBox : sa + kI8Slices * kPBoxA;
-          const uint32_t bstride = inA ? kPBoxA : kPBoxB;
-          const int steps = min(kPKBox / 32, (r + 31) / 32 - kb * (kPKBox / 32));
-          for (int ks = 0; ks < steps; ++ks) {
-            const uint32_t koff = ks * 32;
-            const bool first = (kb | ks) == 0;
-#pragma unroll
-            for (int sgrp = 0; sgrp < kI8Slices; ++sgrp) {
-#pragma unroll
-              for (int p = 0; p <= sgrp; ++p) {
-                const int q = sgrp - p;
-                const uint32_t aa = sa + p * kPBoxA + koff, bb = sb + q * bstride + koff;
-                tc_mma_i8(acc + sgrp * kI8TileN, make_kmajor_sw64_desc(aa), make_kmajor_sw64_desc(bb), kIdescI8, (first && p == 0) ? 0u : 1u);
+        bool grabbed = false;
+        for (int k = 0; k < nt && !timeout; ++k) {
+          const bool first = k == 0 || ts[k] != ts[k - 1] || ti0[k] != ti0[k - 1];
+          const bool last = k == nt - 1 || ts[k + 1] != ts[k] || ti0[k + 1] != ti0[k];
+          const int s = ts[k], i0 = ti0[k], j0 = tj0[k];
+          if (!publish(s, i0, j0, (first ? 1 : 0) | (last ? 2 : 0))) break;
+          const int nkb = (tr[k] + kPKBox - 1) / kPKBox;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (kRes) {
+              if (first) {                                 // this strip's A panel, chunk by chunk (each chunk has its own barriers)
+                bool ok;
+                REKF_T(2, ok = mbar_wait_backoff(&a_empty[kb], (acnt[kb] & 1) ^ 1));
+                if (!ok) { timeout = true; break; }
+                mbar_expect_tx(&a_full[kb], kPChunkA);
+                tma_load_5d(opsA + (size_t)kb * kPChunkA, &map_a, &a_full[kb], 0, i0, kb, 0, s);
+                ++acnt[kb];
               }
+              {
+                const int stage = bcnt & (kPResBStages - 1);
+                bool ok;
+                REKF_T(3, ok = mbar_wait_backoff(&b_empty[stage], ((bcnt / kPResBStages) & 1) ^ 1));
+                if (!ok) { timeout = true; break; }
+                mbar_expect_tx(&b_full[stage], kPChunkB);
+                tma_load_5d(opsB + (size_t)stage * kPChunkB, &map_b, &b_full[stage], 0, j0, kb, 0, s);
+                ++bcnt;
+              }
+            } else {
+              const int stage = bcnt & (kPStrStages - 1);
+              if (!mbar_wait_backoff(&b_empty[stage], ((bcnt / kPStrStages) & 1) ^ 1)) { timeout = true; break; }
+              uint8_t *sa = opsA + (size_t)stage * (kPChunkA + kPChunkB);
+              mbar_expect_tx(&b_full[stage], kPChunkA + kPChunkB);
+              tma_load_5d(sa, &map_a, &b_full[stage], 0, i0, kb, 0, s);
+              tma_load_5d(sa + kPChunkA, &map_b, &b_full[stage], 0, j0, kb, 0, s);
+              ++bcnt;
             }
           }
-          tc_commit(&op_empty[stage]);
+          if (!grabbed) { grab(start, cnt); grabbed = true; }   // one span ahead, behind this span's first loads: the atomic's round trip is hidden
         }
-        tc_commit(&acc_full[set]);
-        ++iter;
+        if (!grabbed) grab(start, cnt);
       }
+      if (!timeout) publish(-1, 0, 0, 0);
+#ifdef REKF_SYRK_TIMING
+      tlog[0] = tacc[1]; tlog[1] = tacc[2]; tlog[2] = tacc[3]; tlog[3] = (double)(clock64() - t_begin); tlog[4] = (double)qn;
+#endif
     }
+  } else if (warp == kPEpiWarps + 1) {
+    // ===== MMA issuer: the whole warp walks the (warp-uniform) loop, one elected lane issues the MMAs and commits.  With the
+    //       loop under `if (lane == 0)` ptxas wrapped each of the 70 MMAs of a tile in a per-active-thread loop of five
+    //       R2UR moves (~100 cycles per MMA: the issue thread, not the tensor pipe, set the tile period). =====
+    uint32_t bcnt = 0, iter = 0, ause[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t q = 0; !timeout; ++q) {
+      int s, i0, j0, flags;
+      if (!next_tile(q, true, s, i0, j0, flags)) break;
+      int r, n;
+      sess_rn(s - L.s0, r, n);
+      const bool first = flags & 1, last = flags & 2;
+      const int set = iter & 1;
+      {
+        bool ok;
+        REKF_T(1, ok = mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1));
+        if (!ok) timeout = true;
+      }
+      tc_fence_after();
+      const uint32_t acc = tmem + set * 256;
+      const int nkb = (r + kPKBox - 1) / kPKBox;
+      for (int kb = 0; kb < nkb; ++kb) {
+        uint32_t sa, sb;
+        int stage;
+        if (kRes) {
+          if (first) {
+            bool ok;
+            REKF_T(2, ok = mbar_wait_backoff(&a_full[kb], ause[kb] & 1));
+            if (!ok) timeout = true;
+          }
+          sa = smem_u32(opsA + (size_t)kb * kPChunkA);
+          stage = bcnt & (kPResBStages - 1);
+          bool ok;
+          REKF_T(3, ok = mbar_wait_backoff(&b_full[stage], (bcnt / kPResBStages) & 1));
+          if (!ok) timeout = true;
+          sb = smem_u32(opsB + (size_t)stage * kPChunkB);
+        } else {
+          stage = bcnt & (kPStrStages - 1);
+          if (!mbar_wait_backoff(&b_full[stage], (bcnt / kPStrStages) & 1)) timeout = true;
+          sa = smem_u32(opsA + (size_t)stage * (kPChunkA + kPChunkB));
+          sb = sa + kPChunkA;
+        }
+        timeout = __any_sync(0xffffffffu, timeout);
+        if (timeout) break;
+        tc_fence_after();
+        const int steps = min(kPKBox / 32, (r + 31) / 32 - kb * (kPKBox / 32));
+        if (elect_one_sync()) {
+          // Per k-step FOUR MMAs instead of ten: the B chunk holds the four digit slices back to back ([slice][64 rows][64 B]),
+          // i.e. it IS a 256-row K-major operand.  A-slice p times its first 64·(4−p) rows (slices q = 0..3−p) with D starting at
+          // accumulator p drops every product d_pᵀ·d_q into accumulator p+q — the same ten 128x64x32 products, but the A
+          // slice is fetched from shared memory once per p, not once per (p, q): 36 KB instead of 60 KB of operand reads per
+          // k-step.  (With ten N=64 MMAs the tile period was set by shared-memory bandwidth: ~87 cycles per MMA against 32.)
+          // Descriptors differ only in the 14-bit start-address field (16-byte units).
+          const uint64_t da = make_kmajor_sw64_desc(sa), db = make_kmajor_sw64_desc(sb);
+          for (int ks = 0; ks < steps; ++ks) {
+            const uint32_t zero = (kb | ks) == 0 ? 0u : 1u;
+            const uint64_t dbk = db + (uint64_t)((ks * 32) >> 4);
+#pragma unroll
+            for (int p = 0; p < kI8Slices; ++p)
+              tc_mma_i8(acc + p * kI8TileN, da + (uint64_t)((p * kPBoxA + ks * 32) >> 4), dbk, idesc_i8(kI8TileN * (kI8Slices - p)),
+                        p == 0 ? zero : 1u);
+          }
+          if (kRes) {
+            tc_commit(&b_empty[stage]);
+            if (last) tc_commit(&a_empty[kb]);             // the panel chunk may be overwritten once these MMAs retire
+          } else {
+            tc_commit(&b_empty[stage]);
+          }
+          if (kb == nkb - 1) tc_commit(&acc_full[set]);
+        }
+        __syncwarp();
+        ++bcnt;
+        if (kRes && last) ++ause[kb];
+      }
+      ++iter;
+    }
+#ifdef REKF_SYRK_TIMING
+    if (lane == 0) { tlog[5] = tacc[0]; tlog[6] = tacc[1]; tlog[7] = tacc[2]; tlog[8] = tacc[3]; tlog[9] = (double)(clock64() - t_begin); }
+#endif
   } else if (warp == kPEpiWarps + 2) {
     // ===== column scales / flags of every tile → shared memory (whole warp).  The slot is the accumulator set's: free
     //       once the epilogue released that set.  Every lane arrives for its own two entries. =====
     uint32_t iter = 0;
     for (uint32_t q = 0; !timeout; ++q) {
-      const int item = next_item(q, true);
-      if (item < 0) break;
-      int s, i0, j0, r, n; bool inA;
-      decode(item, s, i0, j0, r, n, inA);
+      int s, i0, j0, flags;
+      if (!next_tile(q, true, s, i0, j0, flags)) break;
       const int set = iter & 1;
       if (!mbar_wait_backoff(&acc_empty[set], ((iter >> 1) & 1) ^ 1)) timeout = true;
       {
@@ -266,164 +365,113 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
       ++iter;
     }
   } else if (warp == kPEpiWarps + 3) {
-    // ===== Σ reduce-add issuer: waits until the 512 epilogue threads have written a downdate half-tile, hands it to the
-    //       TMA (the L2 adds it into Σ), and frees the slot one group later, when the TMA has read it out =====
+    // ===== Σ reduce-add issuer: waits until the epilogue warps have written a downdate box, hands it to the TMA (the L2
+    //       adds it into Σ) and frees the slot as soon as the TMA has read it out of shared memory =====
     if (lane == 0) {
-      uint32_t sit = 0;
-      int pending = -1;                                    // slot whose reduce has been issued but not yet released
+      uint32_t u = 0;
       for (uint32_t q = 0; !timeout; ++q) {
-        const int item = next_item(q, false);
-        if (item < 0) break;
-        int s, i0, j0, r, n; bool inA;
-        decode(item, s, i0, j0, r, n, inA);
-        if (inA) {
-          if (pending >= 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            mbar_arrive(&sig_empty[pending]);
-            pending = -1;
-          }
-          continue;
-        }
-        for (int h = 0; h < 2; ++h) {
-          const int slot = ((sit & 1) << 1) | h;
-          if (!mbar_wait_backoff(&sig_done[slot], (sit >> 1) & 1)) { timeout = true; break; }
-          const uint8_t *src = sig + (size_t)slot * kPSigHalf;
-          tma_reduce_add_3d(&map_sig, src, j0 + 32 * h, i0, s);
-          tma_reduce_add_3d(&map_sig, src + kPSigHalf / 2, j0 + 32 * h + 16, i0, s);
+        int s, i0, j0, flags;
+        if (!next_tile(q, false, s, i0, j0, flags)) break;
+        for (int qd = 0; qd < 4; ++qd, ++u) {
+          const int slot = u & (kPSigSlots - 1);
+          bool ok;
+          REKF_T(1, ok = mbar_wait_backoff(&sig_done[slot], (u / kPSigSlots) & 1));
+          if (!ok) { timeout = true; break; }
+          tma_reduce_add_3d(&map_sig, sig + (size_t)slot * kPSigBox, j0 + 16 * qd, i0, s);
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (pending >= 0) {
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // every group but the one just issued
-            mbar_arrive(&sig_empty[pending]);
-          }
-          pending = slot;
+          REKF_T(2, asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"));
+          mbar_arrive(&sig_empty[slot]);
         }
-        ++sit;
       }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all reductions performed
+      REKF_T(3, asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"));   // all reductions performed
+#ifdef REKF_SYRK_TIMING
+      tlog[10] = tacc[0]; tlog[11] = tacc[1]; tlog[12] = tacc[2]; tlog[13] = tacc[3]; tlog[14] = (double)(clock64() - t_begin);
+#endif
     }
   } else if (warp < kPEpiWarps) {
-    // ===== epilogue: warp w owns TMEM lanes 32·(w%4).. ; within a 32-column half-tile, columns 8·(w/4).. .  Sixteen warps
-    //       (four per scheduler) because the per-element chain — TMEM load, integer recombination, int→fp64, scale, FMA —
-    //       is latency-bound: with eight warps the epilogue, not HBM, set the tile period =====
-    const int quad = warp & 3, cgp = warp >> 2;
+    // ===== epilogue: warp w owns TMEM lanes 32·(w%4).. and columns 4·(w/4).. of every 16-column box.  Sixteen warps (four per
+    //       scheduler) because the per-element chain — TMEM load, integer recombination, int→fp64, scale — is latency-bound =====
+    const int quad = warp & 3, cg = warp >> 2;
     const int il = quad * 32 + lane;                     // row inside the tile
-    uint32_t iter = 0, sit = 0;
+    uint32_t iter = 0, u = 0;
     const int ld = L.ld;
-    int row_s = -1, row_i0 = -1;                         // row scale / flag are reloaded only when the row block changes
-    double si = 0.0;
+    int row_s = -1, row_i0 = -1;                         // row scale / flag / exact diagonal: reloaded when the row block changes
+    double si = 0.0, wd = 0.0;
     bool row_ok = false;
     for (uint32_t q = 0;; ++q) {
-      const int item = next_item(q, true);
-      if (item < 0) break;
-      int s, i0, j0, r, n; bool inA;
-      decode(item, s, i0, j0, r, n, inA);
+      int s, i0, j0, flags;
+      if (!next_tile(q, true, s, i0, j0, flags)) break;
       const int set = iter & 1;
       const int i = i0 + il;
-      double *Sg = L.sigma + (size_t)s * ld * ld;
+      const bool inA = j0 < i0 + 128;
       if (s != row_s || i0 != row_i0) {
         si = L.Wscale[(size_t)s * ld + i] * 0x1p-35;
         row_ok = !L.Wflag[(size_t)s * ld + i];
+        wd = L.Wdiag[(size_t)s * ld + i];
         row_s = s; row_i0 = i0;
       }
       const double *sct = sc_tab + set * 64;
       const unsigned char *flt = fl_tab + set * 64;
-      if (!mbar_wait(&sc_full[set], (iter >> 1) & 1)) timeout = true;
-      if (!mbar_wait(&acc_full[set], (iter >> 1) & 1)) timeout = true;
+      REKF_T(1, if (!mbar_wait(&sc_full[set], (iter >> 1) & 1)) timeout = true);
+      REKF_T(2, if (!mbar_wait(&acc_full[set], (iter >> 1) & 1)) timeout = true);
       tc_fence_after();
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int col0 = 32 * h + 8 * cgp;               // first of this thread's 8 tile columns
-        const int jbase = j0 + col0;
-        const uint32_t taddr = tmem + set * 256 + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0;
-        // s32 accumulators of the four digit groups, all four loads in flight; groups are recombined pairwise in 32 bits
-        // (|acc| < 2^23 for K <= 512, so acc·2^7 + acc' fits), then once in 64 bits: G = Σ_g acc_g · 2^(7·(3-g))
-        long long G[8];
-        {
-          uint32_t g0[8], g1[8], g2[8], g3[8];
-          tc_ld8(taddr, g0);
-          tc_ld8(taddr + kI8TileN, g1);
-          tc_ld8(taddr + 2 * kI8TileN, g2);
-          tc_ld8(taddr + 3 * kI8TileN, g3);
-          tc_wait_ld();
+      // the TMEM loads of box qd+1 are in flight while box qd is converted, written and handed over (TMEM reads run at
+      // 64 B/clk per SM: 512 cycles per box for the four s32 accumulators — the floor of this loop)
+      uint32_t g[2][4][4];
+      const uint32_t tbase = tmem + set * 256 + ((uint32_t)(quad * 32) << 16) + (uint32_t)(4 * cg);
+      auto issue_ld = [&](int qd, int buf) {
 #pragma unroll
-          for (int u = 0; u < 8; ++u)
-            G[u] = ((long long)(((int)g0[u] << 7) + (int)g1[u]) << 14) + (long long)(((int)g2[u] << 7) + (int)g3[u]);
+        for (int a = 0; a < 4; ++a) tc_ld4(tbase + 16 * qd + a * kI8TileN, g[buf][a]);
+      };
+      issue_ld(0, 0);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd, ++u) {
+        const int buf = qd & 1;
+        const int col0 = 16 * qd + 4 * cg;               // first of this thread's 4 tile columns
+        tc_wait_ld();
+        if (qd < 3) issue_ld(qd + 1, buf ^ 1);
+        const uint32_t cf = *reinterpret_cast<const uint32_t *>(flt + col0);
+        const double2 sj0 = *reinterpret_cast<const double2 *>(sct + col0), sj1 = *reinterpret_cast<const double2 *>(sct + col0 + 2);
+        const double sj[4] = {sj0.x, sj0.y, sj1.x, sj1.y};
+        double cur[4];
+        // groups are recombined pairwise in 32 bits (|acc| < 2^23 for K <= 512, so acc·2^7 + acc' fits), then once in 64 bits:
+        // G = Σ_a acc_a · 2^(7·(3-a))
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const long long G = ((long long)(((int)g[buf][0][e] << 7) + (int)g[buf][1][e]) << 14) +
+                              (long long)(((int)g[buf][2][e] << 7) + (int)g[buf][3][e]);
+          cur[e] = -i64_to_f64(G) * (si * sj[e]);          // exact: an integer below 2^51 times a power of two
         }
-        const uint2 cf = *reinterpret_cast<const uint2 *>(flt + col0);
-        const double2 *scj = reinterpret_cast<const double2 *>(sct + col0);
-        double cur[8];
-        if (!inA) {
-          // ---- downdate half-tile: −G·2^(e_i+e_j) (exact) into the swizzled staging slot; the TMA reduce adds it into Σ ----
-          const int slot = ((sit & 1) << 1) | h;
-          if (!mbar_wait(&sig_empty[slot], ((sit >> 1) & 1) ^ 1)) timeout = true;   // the previous reduce has read it out
-          uint8_t *rowp = sig + (size_t)slot * kPSigHalf + (size_t)(cgp >> 1) * (kPSigHalf / 2) + (size_t)il * 128;
-          const int ch0 = 4 * (cgp & 1);                  // this thread's four 16-byte chunks of the 128-byte row
-          const bool no_flags = row_ok && (cf.x | cf.y) == 0u;   // the common case, warp-uniform but for row_ok
-          if (no_flags) {
+        if (!row_ok || cf != 0u || inA) {                  // rare: flagged slots (k_syrk_exact_rows did them), diagonal tiles
+          const int jb = j0 + col0;
 #pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-              const double2 sj = scj[u >> 1];
-              cur[u] = -i64_to_f64(G[u]) * (si * sj.x);
-              cur[u + 1] = -i64_to_f64(G[u + 1]) * (si * sj.y);
-            }
-          } else {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const unsigned cfw = (u < 4) ? cf.x : cf.y;
-              const bool skip = !row_ok || ((cfw >> (8 * (u & 3))) & 0xffu);   // flagged slots: k_syrk_exact_rows did them
-              cur[u] = skip ? 0.0 : -i64_to_f64(G[u]) * (si * sct[col0 + u]);
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<double2 *>(rowp + (((ch0 + c) ^ (il & 7)) << 4)) = make_double2(cur[2 * c], cur[2 * c + 1]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(&sig_done[slot]);                     // hand the half-tile to the reduce issuer
-        } else {
-          // ---- diagonal tile: direct global accesses, element predicates (i <= j), exact diagonal ----
-          const bool want = row_ok && i < n && jbase < n && !(jbase + 7 < i);
-          if (want) {
-            double *row = Sg + (size_t)i * ld + jbase;
-            ldg256(row, cur);
-            ldg256(row + 4, cur + 4);
-            const int ud = i - jbase;
-            double old_diag = 0.0;
-#pragma unroll
-            for (int u = 0; u < 8; u += 2) {
-              const double2 sj = scj[u >> 1];
-              if (u == ud) old_diag = cur[u];
-              if (u + 1 == ud) old_diag = cur[u + 1];
-              cur[u] = fma(-i64_to_f64(G[u]), si * sj.x, cur[u]);
-              cur[u + 1] = fma(-i64_to_f64(G[u + 1]), si * sj.y, cur[u + 1]);
-            }
-            if (ud >= 0 && ud < 8) {
-              const double dd = old_diag - L.Wdiag[(size_t)s * ld + i];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) if (u == ud) cur[u] = dd;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = jbase + u;
-              const unsigned cfw = (u < 4) ? cf.x : cf.y;
-              if (j < n && i <= j && !((cfw >> (8 * (u & 3))) & 0xffu)) row[u] = cur[u];
-            }
+          for (int e = 0; e < 4; ++e) {
+            const bool skip = !row_ok || ((cf >> (8 * e)) & 0xffu) || i > jb + e;
+            if (i == jb + e) cur[e] = -wd;                 // the diagonal: exact fp64 sum of squares
+            if (skip) cur[e] = 0.0;
           }
         }
+        const int slot = u & (kPSigSlots - 1);
+        REKF_T(3, if (!mbar_wait(&sig_empty[slot], ((u / kPSigSlots) & 1) ^ 1)) timeout = true);   // the previous reduce has read it out
+        uint8_t *rowp = sig + (size_t)slot * kPSigBox + (size_t)il * 128;
+        *reinterpret_cast<double2 *>(rowp + (((2 * cg) ^ (il & 7)) << 4)) = make_double2(cur[0], cur[1]);
+        *reinterpret_cast<double2 *>(rowp + (((2 * cg + 1) ^ (il & 7)) << 4)) = make_double2(cur[2], cur[3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sig_done[slot]);       // hand the box to the reduce issuer
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[set]);                      // this thread is done with the accumulator set
-#ifdef REKF_SYRK_TIMING
-      if (threadIdx.x == 0) { const double t = gtime(); if (iter == 0) tlog[2] = t; tlog[3] = t; tlog[5] += 1; }
-#endif
+      mbar_arrive(&acc_empty[set]);                        // this thread is done with the accumulator set
       ++iter;
-      if (!inA) ++sit;
     }
+#ifdef REKF_SYRK_TIMING
+    if (threadIdx.x == 0) {
+      tlog[15] = tacc[0]; tlog[16] = tacc[1]; tlog[17] = tacc[2]; tlog[18] = tacc[3]; tlog[19] = (double)(clock64() - t_begin); tlog[20] = (double)iter;
+    }
+#endif
   }
   if (timeout) atomicOr(&L.st[L.s0].flags, FLAG_TCGEN05_TIMEOUT);
   __syncthreads();
-#ifdef REKF_SYRK_TIMING
-  if (threadIdx.x == 0) tlog[4] = gtime();
-#endif
   if (warp == kPEpiWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
@@ -458,7 +506,9 @@ inline const char *syrk_i8p_init(SyrkI8P &tc, const Layout &L) {
   if (encode(&tc.map_sig, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, L.sigma, sdims, sstrides, sbox, sestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return "cuTensorMapEncodeTiled(Sigma) failed";
-  if (cudaFuncSetAttribute(k_syrk_tcgen05_i8p, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemBytes) != cudaSuccess)
+  tc.resident = L.kq <= kPResChunks * kPKBox;
+  if (cudaFuncSetAttribute(k_syrk_tcgen05_i8p<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemRes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_syrk_tcgen05_i8p<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmemStr) != cudaSuccess)
     return "cudaFuncSetAttribute(k_syrk_tcgen05_i8p, smem) failed";
   int dev = 0;
   cudaGetDevice(&dev);
@@ -472,7 +522,8 @@ inline int syrk_i8p_launch(const SyrkI8P &tc, const Layout &L, cudaStream_t stre
   const int total = (L.ld / 128) * (L.ld / 128 + 1) * L.Sg;
   const int ctas = tc.num_sms - tc.reserve_sms > 1 ? tc.num_sms - tc.reserve_sms : 1;
   const int grid = total < ctas ? total : ctas;
-  k_syrk_tcgen05_i8p<<<grid, kPThreads, kPSmemBytes, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
+  if (tc.resident) k_syrk_tcgen05_i8p<true><<<grid, kPThreads, kPSmemRes, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
+  else k_syrk_tcgen05_i8p<false><<<grid, kPThreads, kPSmemStr, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
   return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
