@@ -9,13 +9,20 @@
 // The reference class keeps μ and Σ in host Eigen storage and hands out mutable references
 // (reflector_ekf_slam.h:25-32).  Here the state lives in HBM; the adapter keeps a host mirror that is
 // refreshed lazily — only when a getter is called after the state changed — so a node that reads
-// GetState() after every message (ros_node.cc:478,515,592,638) pays one device→host copy per message,
-// like the by-value copy it pays today.  Writes through the returned references are NOT pushed back to
-// the device (the node never writes through them).
+// GetState() after every message (ros_node.cc:478,515,592,638) pays one device→host copy per message
+// (rekf_get_state: one stream synchronisation; the covariance mirror is page-locked so the copy runs at
+// PCIe speed), like the by-value copy it pays today.  Writes through the returned references are NOT
+// pushed back to the device (the node never writes through them).  A node that only needs the pose and
+// the markers should call GetPose() / GetMarkers() instead: 96 bytes instead of n² doubles per message.
 //
 // Error convention: the reference logs and calls exit(-1) (reflector_ekf_slam.cc:376-377); the C ABI
 // returns status codes; this adapter prints rekf_last_error() to stderr and calls std::exit(-1) for
 // fatal codes, and keeps the reference's silent behaviour for stale odometry / missing map files.
+// The engine's sticky device flags travel with every state read: a landmark-capacity overflow (the
+// reference grows without bound, :316-363; the engine's capacity is the constructor's max_landmarks), an
+// innovation matrix that lost positive definiteness or a tensor-kernel timeout are reported on stderr
+// once and — being unrecoverable divergences from the reference — end the process like the reference's
+// own fatal paths.
 #ifndef REFLECTOR_EKF_SLAM_REFLECTOR_EKF_SLAM_B200_H
 #define REFLECTOR_EKF_SLAM_REFLECTOR_EKF_SLAM_B200_H
 
@@ -40,7 +47,7 @@ public:
   // are engine-only (the reference grows its Eigen matrices on demand, :320).
   explicit ReflectorEKFSLAMB200(const EKFOptions &options, int max_landmarks = 1024, int max_observations = 128,
                                 int device = 0)
-      : handle_(nullptr), mu_stale_(true), sigma_stale_(true)
+      : handle_(nullptr), mu_stale_(true), sigma_stale_(true), pinned_(nullptr)
   {
     rekf_options o;
     rekf_default_options(&o);
@@ -62,7 +69,12 @@ public:
   ReflectorEKFSLAMB200() = delete;
   ReflectorEKFSLAMB200(const ReflectorEKFSLAMB200 &) = delete;
   ReflectorEKFSLAMB200 &operator=(const ReflectorEKFSLAMB200 &) = delete;
-  ~ReflectorEKFSLAMB200() override { rekf_destroy(handle_); }
+  ~ReflectorEKFSLAMB200() override
+  {
+    if (pinned_)
+      rekf_host_unregister(handle_, pinned_);
+    rekf_destroy(handle_);
+  }
 
   // reflector_ekf_slam.cc:208-223
   void HandleOdometryMessage(const sensor::OdometryData &odometry) override
@@ -101,14 +113,14 @@ public:
   {
     State out;
     const int n = Dim();
-    out.time = time;
+    out.time = GetLatestTime();   // :99 `result = state_` and the time is never advanced: the reference returns state_.time
     out.mu.resize(n);
     out.sigma.resize(n, n);
     Check(rekf_predict_state(handle_, 0, time, out.mu.data(), n, out.sigma.data(), n), "rekf_predict_state");
     return out;
   }
-  Eigen::VectorXd &GetStateVector() override { RefreshMu(); return mirror_.mu; }
-  Eigen::MatrixXd &GetCoviarance() override { RefreshSigma(); return mirror_.sigma; }
+  Eigen::VectorXd &GetStateVector() override { Refresh(false); return mirror_.mu; }
+  Eigen::MatrixXd &GetCoviarance() override { Refresh(true); return mirror_.sigma; }
   double GetLatestTime() override
   {
     double t = 0.;
@@ -117,9 +129,7 @@ public:
   }
   State GetState() override
   {
-    RefreshMu();
-    RefreshSigma();
-    mirror_.time = GetLatestTime();
+    Refresh(true);
     return mirror_;
   }
   sensor::Map GetGlobalMap() override
@@ -144,6 +154,16 @@ public:
   // ---- engine extras (not part of the reference interface) -----------------------------------------
   // pose + 3x3 block without pulling the whole covariance (what ros_node.cc:802-817 publishes)
   void GetPose(double pose[3], double cov33[9]) { Check(rekf_get_pose(handle_, 0, pose, cov33), "rekf_get_pose"); }
+  // Node::ReflectorToRosMarkers (ros_node.cc:736-789) evaluated on the device: x, y, angle, x_len, y_len per landmark
+  int GetMarkers(std::vector<double> &markers)
+  {
+    int count = 0;
+    Check(rekf_get_markers(handle_, 0, nullptr, 0, &count), "rekf_get_markers");
+    markers.resize(5 * static_cast<size_t>(count > 0 ? count : 1));
+    if (count > 0)
+      Check(rekf_get_markers(handle_, 0, markers.data(), count, &count), "rekf_get_markers");
+    return count;
+  }
   // Node::SaveReflectorResult (ros_node.cc:75-140) without the host-side State copy
   bool SaveMapTxt(const std::string &filebase) { return rekf_save_map_txt(handle_, 0, filebase.c_str()) == REKF_OK; }
   // feed observation.gps_pose_ as the three pose rows of reflector_ekf_slam_gps.cc:305-340
@@ -158,24 +178,56 @@ private:
       Check(n, "rekf_dim");
     return n;
   }
-  void RefreshMu()
+  // one rekf_get_state per stale read; a second one when the state has grown since the mirror was sized
+  void Refresh(bool want_sigma)
   {
-    if (!mu_stale_)
+    if (!mu_stale_ && (!want_sigma || !sigma_stale_))
       return;
-    const int n = Dim();
-    mirror_.mu.resize(n);
-    int got = 0;
-    Check(rekf_get_mu(handle_, 0, mirror_.mu.data(), n, &got), "rekf_get_mu");
-    mu_stale_ = false;
+    for (int attempt = 0; attempt < 2; ++attempt)
+    {
+      int n = static_cast<int>(mirror_.mu.rows());
+      if (n < 3)
+        n = Dim();
+      ResizeMirror(n, want_sigma);
+      int n_now = 0, flags = 0;
+      const int rc = rekf_get_state(handle_, 0, n, &mirror_.time, mirror_.mu.data(), want_sigma ? mirror_.sigma.data() : nullptr, n,
+                                    &n_now, &flags);
+      if (flags != 0)
+      {
+        std::fprintf(stderr, "[rekf_b200] device flags 0x%x (1: landmark capacity exceeded, 2: S not positive definite, 4: observation "
+                             "capacity exceeded, 8: tensor-kernel timeout) - the filter no longer follows the reference\n", flags);
+        std::exit(-1);
+      }
+      if (rc == REKF_ERR_CAPACITY && n_now >= 3 && n_now != n)
+      {
+        ResizeMirror(n_now, want_sigma);
+        continue;
+      }
+      Check(rc, "rekf_get_state");
+      mu_stale_ = false;
+      if (want_sigma)
+        sigma_stale_ = false;
+      return;
+    }
+    Check(REKF_ERR_CAPACITY, "rekf_get_state (state kept growing)");
   }
-  void RefreshSigma()
+  void ResizeMirror(int n, bool want_sigma)
   {
-    if (!sigma_stale_)
-      return;
-    const int n = Dim();
-    mirror_.sigma.resize(n, n);
-    Check(rekf_get_sigma(handle_, 0, mirror_.sigma.data(), n), "rekf_get_sigma");   // column-major like MatrixXd
-    sigma_stale_ = false;
+    if (mirror_.mu.rows() != n)
+    {
+      mirror_.mu.resize(n);
+      mu_stale_ = sigma_stale_ = true;
+    }
+    if (want_sigma && (mirror_.sigma.rows() != n || mirror_.sigma.cols() != n))
+    {
+      if (pinned_)
+        rekf_host_unregister(handle_, pinned_);
+      mirror_.sigma.resize(n, n);
+      sigma_stale_ = true;
+      pinned_ = mirror_.sigma.data();
+      if (rekf_host_register(handle_, pinned_, sizeof(double) * static_cast<size_t>(n) * n) != REKF_OK)
+        pinned_ = nullptr;   // pageable copies still work, only slower
+    }
   }
   void Check(int rc, const char *what)
   {
@@ -188,6 +240,7 @@ private:
   rekf_handle *handle_;
   State mirror_;
   bool mu_stale_, sigma_stale_;
+  void *pinned_;   // the covariance mirror's buffer while it is page-locked
   bool use_gps_rows_ = false;
   std::vector<float> scratch_;
 };

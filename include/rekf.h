@@ -87,7 +87,8 @@ typedef struct rekf_options {
   double observation_cov;
   /* --- engine-only --- */
   int max_landmarks;             /* capacity N_cap of the state (landmarks); default 1024 if 0 */
-  int max_observations;          /* capacity of one observation frame; default 128 if 0 (max 512) */
+  int max_observations;          /* capacity of one observation frame; default 128 if 0.  Bounded by the shared memory of
+                                    the Cholesky / TRSM kernels: about 400; rekf_create fails with REKF_ERR_CAPACITY above */
   int max_map_landmarks;         /* capacity of the pre-loaded beacon map; default 1024 if 0 */
   int device;                    /* CUDA device ordinal */
   int cov_update;                /* REKF_COV_* */
@@ -122,7 +123,8 @@ REKF_API int rekf_sessions(const rekf_handle *h);
 REKF_API int rekf_handle_odometry(rekf_handle *h, double time, double vx, double vy, double wz);
 /* HandleObservationMessage(const sensor::Observation&) (:229-368): predict to `time`, associate,
  * update, augment.  xy = m float32 pairs in base_link; m may be 0 (predict only, :235).
- * gps_pose_or_null: reserved for the USE_GPS variant (reflector_ekf_slam_gps.cc:305-340); pass NULL. */
+ * gps_pose_or_null: NULL, or the (x, y, yaw) pose of the USE_GPS variant (ekf::ReflectorEKFSLAMGPS,
+ * reflector_ekf_slam_gps.cc:305-340): three extra measurement rows on the pose, applied when the frame has matches. */
 REKF_API int rekf_handle_observation(rekf_handle *h, double time, const float *xy, int m,
                                      const double *gps_pose_or_null);
 /* HandleImuMessage (:224-227) is empty in every reference implementation. */
@@ -176,6 +178,20 @@ REKF_API int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double 
 REKF_API int rekf_get_markers(rekf_handle *h, int session, double *markers, int cap, int *count_out);
 /* GetCoviarance() (reflector_ekf_slam.h:29-32): full n x n, column-major, leading dimension ld >= n. */
 REKF_API int rekf_get_sigma(rekf_handle *h, int session, double *sigma, int ld);
+/* GetState() (reflector_ekf_slam.h:37-40; the node calls it after every message, ros_node.cc:478,515,592,638) in one
+ * stream synchronisation: time, mu (n doubles), sigma (n x n column-major, ld >= n; may be NULL) and the sticky device
+ * flags (*flags_out != 0: capacity overflow / S not SPD / tensor-kernel timeout — see rekf_sync).  n_expect is the
+ * dimension the caller's buffers are sized for; if the state has a different dimension nothing is copied, *n_out
+ * reports it and the call returns REKF_ERR_CAPACITY (resize and repeat). */
+REKF_API int rekf_get_state(rekf_handle *h, int session, int n_expect, double *time_out, double *mu, double *sigma,
+                            int ld, int *n_out, int *flags_out);
+/* Page-lock / release a caller-owned host buffer that rekf_get_state / rekf_get_sigma copy into (the adapter's
+ * covariance mirror): device-to-host copies then run at PCIe speed.  Optional. */
+REKF_API int rekf_host_register(rekf_handle *h, void *ptr, size_t bytes);
+REKF_API int rekf_host_unregister(rekf_handle *h, void *ptr);
+/* Cumulative per-session counters since creation / rekf_set_state: out[0] frames with an update, out[1] of those taken
+ * by the fp64 SYRK as a whole (int8 mode: deep cancellation), out[2] flagged slots redone in fp64 in the other frames. */
+REKF_API int rekf_get_counters(rekf_handle *h, int session, int64_t out[3]);
 /* ReflectorMatchResult of the last observation frame (ekf_slam_interface.h:18-26); pairs are
  * {observation index, landmark index} as the reference stores them (:422, :448).  Each array may be
  * NULL; cap is the capacity (in pairs / ids) of every non-NULL array. */

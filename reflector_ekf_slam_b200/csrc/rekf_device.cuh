@@ -51,6 +51,10 @@ struct SessionState {
   unsigned ticket;      // last-block-done counter (augment kernel)
   int exact_update;     // this frame's downdate cancels too deeply for the int8 slices: use the fp64 SYRK
   int exact_slots;      // slots whose rows/columns of the downdate are done in fp64 this frame (k_syrk_exact_rows)
+  // cumulative since creation / rekf_set_state (rekf_get_counters): how often the int8 covariance update left the tensor path
+  long long n_updates;        // frames that carried an update (r > 0)
+  long long n_exact_frames;   // of those: whole frame on the fp64 SYRK (exact_update)
+  long long n_exact_slots;    // flagged slots handled by k_syrk_exact_rows, summed over the other frames
 };
 
 // Where the current message comes from: the handle's device mailbox (host path) or device-resident

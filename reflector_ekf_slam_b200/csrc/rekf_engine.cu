@@ -28,9 +28,9 @@ using namespace rekf;
 
 namespace {
 
-enum KernelId { K_ODOM = 0, K_FRONT, K_INNOV, K_CHOL, K_SOLVE, K_SYRK, K_AUGMENT, K_COUNT };
+enum KernelId { K_ODOM = 0, K_FRONT, K_INNOV, K_CHOL, K_SOLVE, K_SYRK_EXACT, K_SYRK, K_AUGMENT, K_COUNT };
 const char *kKernelNames[K_COUNT] = {"k_odometry", "k_observation_front", "k_innovation", "k_cholesky",
-                                     "k_solve_w", "k_syrk", "k_augment"};
+                                     "k_solve_w", "k_syrk_exact_rows", "k_syrk", "k_augment"};
 
 struct ProfRecord { int id; cudaEvent_t a, b; };
 
@@ -53,6 +53,7 @@ struct Group {
   cudaEvent_t slot_done[kSlots]{};
   int slot = 0;
   InputRef host_in{};
+  InputRef *replay_in_dev = nullptr;   // the replay graphs read their input descriptor from here (InputRef::indirect)
   // replay graph (one step of this group)
   // one step (odometry + observation message) as CUDA graph(s): for the device-resident replay and for the host-message
   // step call (the mailbox is at a fixed address, so that chain is static too)
@@ -88,6 +89,7 @@ struct rekf_handle {
   // staging for getters / setters
   double *stage_dev = nullptr;
   size_t stage_elems = 0;
+  double *hdr_host = nullptr;   // pinned: header of rekf_get_state
   // host copy of the beacon map
   std::vector<float> map_xy;
   std::vector<double> map_cov;
@@ -106,6 +108,23 @@ struct rekf_handle {
 };
 
 namespace {
+
+// Every entry point runs on the handle's device, whatever the calling thread's current device is (a ROS node's
+// callback and service threads default to device 0), and leaves the caller's current device untouched.
+struct DeviceGuard {
+  int prev = -1, want = -1;
+  explicit DeviceGuard(const rekf_handle *h) {
+    if (!h) return;
+    want = h->device;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != want) cudaSetDevice(want);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0 && prev != want) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
 
 int fail(rekf_handle *h, int code, const char *fmt, ...) {
   if (h) {
@@ -266,15 +285,17 @@ int launch_obs_wide(rekf_handle *h, Group &grp, const InputRef &in) {
     if (h->solve_w2) k_solve_w3<<<dim3(L.ld / kW3Cols, 1, L.Sg), 256, smem_solve_w3(L.rld), stream>>>(L);
     else k_solve_w<<<dim3(L.ld / kWCols, 1, L.Sg), 256, smem_solve(L), stream>>>(L);
   }
+  if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
+    // fp64 side of the hybrid: the whole frame if st.exact_update, else the rows/columns of flagged slots, else nothing
+    // (it also rewinds the tile cursor of the persistent kernel that follows)
+    ProfScope p(h, K_SYRK_EXACT, stream);
+    k_syrk_f64<<<dim3(148, 1, L.Sg), 256, 0, stream>>>(L);
+  }
   {
     ProfScope p(h, K_SYRK, stream);
     if (h->opts.cov_update == REKF_COV_SIMT_F64) {
       k_syrk_f64<<<dim3(592, 1, L.Sg), 256, 0, stream>>>(L);
     } else if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
-      // fp64 side of the hybrid: the whole frame if st.exact_update, else the rows/columns of flagged slots, else nothing
-      // (it also rewinds the tile queue of the persistent kernel that follows)
-      k_syrk_f64<<<dim3(148, 1, L.Sg), 256, 0, stream>>>(L);
-      ++h->launches;                                              // two kernels inside this scope
       SyrkI8P tc8p = h->tc8p;
       if (&grp == &h->whole) tc8p.reserve_sms = 0;                // nothing else is running beside the whole batch
       int rc = syrk_i8p_launch(tc8p, L, stream);
@@ -317,8 +338,10 @@ int capture_step(rekf_handle *h, Group &g, const InputRef &in, Group::StepGraphs
     cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
     if (rc) return rc;
     if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
-    CK(cudaGraphInstantiate(part == 0 ? &gs.step : &gs.wide, cg, 0));
+    cudaGraphExec_t *exec = part == 0 ? &gs.step : &gs.wide;
+    CK(cudaGraphInstantiate(exec, cg, 0));
     cudaGraphDestroy(cg);
+    CK(cudaGraphUpload(*exec, g.stream));
   }
   gs.in = in;
   gs.launches = h->launches - before;          // kernel nodes per step
@@ -388,6 +411,7 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   g.mb_bytes = round_up((int)(g.off_xy + S * L.mcap * 2 * sizeof(float)), 256);
   int rc = 0;
   if ((rc = dev_alloc(h, &g.mb_dev, g.mb_bytes))) return rc;
+  if ((rc = dev_alloc(h, &g.replay_in_dev, 1))) return rc;
   CK(cudaMallocHost(&g.mb_host, g.mb_bytes * Group::kSlots));
   std::memset(g.mb_host, 0, g.mb_bytes * Group::kSlots);
   for (int i = 0; i < Group::kSlots; ++i) CK(cudaEventCreateWithFlags(&g.slot_done[i], cudaEventDisableTiming));
@@ -463,7 +487,15 @@ const char *rekf_version(void) { return "rekf-b200 0.1 (sm_100a)"; }
 
 int rekf_create(const rekf_options *opts, rekf_handle **out) { return rekf_create_batch(opts, 1, out); }
 
+static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle **out);
 int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out) {
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  const int rc = create_batch_impl(opts, sessions, out);
+  if (prev >= 0) cudaSetDevice(prev);            // the caller's current device is left as it was
+  return rc;
+}
+static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle **out) {
   if (!opts || !out || sessions < 1) return REKF_ERR_BAD_ARGUMENT;
   *out = nullptr;
   rekf_handle *h = new rekf_handle();
@@ -573,6 +605,9 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   CK(cudaEventCreate(&h->t1));
   // opt in to large dynamic shared memory where needed
   if (smem_front(L) > 200 * 1024) return fail(h, REKF_ERR_CAPACITY, "max_landmarks %d needs %zu B of shared memory in k_observation_front", L.Ncap, smem_front(L));
+  if (smem_chol(L) > 227 * 1024 || smem_solve(L) > 227 * 1024)
+    return fail(h, REKF_ERR_CAPACITY, "max_observations %d needs %zu / %zu B of shared memory in the Cholesky / TRSM kernels (limit 227 KB: about 400 observations)",
+                L.mcap, smem_chol(L), smem_solve(L));
   CK(cudaFuncSetAttribute(k_observation_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_front(L)));
   CK(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol(L)));
   h->solve_w2 = smem_solve_w3(L.rld) <= 227 * 1024;
@@ -583,7 +618,6 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
   if (h->chol_resident)
     CK(cudaFuncSetAttribute(k_cholesky_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(L.rcap)));
   CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
-  if (smem_chol(L) > 227 * 1024) return fail(h, REKF_ERR_CAPACITY, "max_observations %d needs %zu B of shared memory in k_cholesky", L.mcap, smem_chol(L));
   if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
     const char *why = syrk_tc_init(h->tc, L);
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK setup failed: %s", why);
@@ -601,6 +635,7 @@ int rekf_create_batch(const rekf_options *opts, int sessions, rekf_handle **out)
 }
 
 int rekf_destroy(rekf_handle *h) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_OK;
   if (h->stream) join_all(h);
   drain_profile(h);
@@ -609,6 +644,7 @@ int rekf_destroy(rekf_handle *h) {
   syrk_tc_destroy(h->tc);
   for (void *p : h->allocations) cudaFree(p);
   if (h->stage_dev) cudaFree(h->stage_dev);
+  if (h->hdr_host) cudaFreeHost(h->hdr_host);
   for (auto &e : h->event_pool) cudaEventDestroy(e);
   if (h->t0) cudaEventDestroy(h->t0);
   if (h->t1) cudaEventDestroy(h->t1);
@@ -624,8 +660,8 @@ void *rekf_stream(rekf_handle *h) { return h ? h->stream : nullptr; }
 
 // ---- hot path -------------------------------------------------------------------------------
 int rekf_batch_handle_odometry(rekf_handle *h, const double *odom) {
+  DeviceGuard dev_guard(h);
   if (!h || !odom) return REKF_ERR_BAD_ARGUMENT;
-  CK(cudaSetDevice(h->device));
   if (h->opts.use_imu) return REKF_OK;   // :213-222: with use_imu the reference does nothing
   for (Group *gp : active_groups(h)) {
     Group &g = *gp;
@@ -650,7 +686,7 @@ int rekf_handle_odometry(rekf_handle *h, double time, double vx, double vy, doub
 static int observation_common(rekf_handle *h, const double *times, const float *xy, const int *counts,
                               int m_stride, const double *gps /*S x 4 or null*/, const double *odom = nullptr /*S x 4: fused step*/) {
   const Layout &L = h->L;
-  CK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h);
   for (int s = 0; s < L.S; ++s) {
     if (counts[s] < 0) return fail(h, REKF_ERR_BAD_ARGUMENT, "negative observation count");
     if (counts[s] > L.mcap) return fail(h, REKF_ERR_CAPACITY, "frame of %d observations exceeds max_observations %d", counts[s], L.mcap);
@@ -715,10 +751,10 @@ int rekf_handle_observation(rekf_handle *h, double time, const float *xy, int m,
 int rekf_handle_imu(rekf_handle *h, double) { return h ? REKF_OK : REKF_ERR_BAD_ARGUMENT; }   // :224-227 empty
 
 int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_time, const void *d_obs_xy, int T, int m, void *d_pose_out) {
+  DeviceGuard dev_guard(h);
   if (!h || !d_odom || !d_obs_time || !d_obs_xy || T < 0 || m < 0) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
   if (m > L.mcap) return fail(h, REKF_ERR_CAPACITY, "m %d exceeds max_observations %d", m, L.mcap);
-  CK(cudaSetDevice(h->device));
   const bool graphs = h->opts.use_graphs && !h->profiling;
   std::vector<Group *> act = active_groups(h);
   std::vector<InputRef> ins(act.size());
@@ -737,12 +773,17 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     in.m_stride = m;
     in.m_fixed = m;
     in.step = g.L.step;
-    in.fuse_odom = 1;
+    in.fuse_odom = h->opts.use_imu ? 0 : 1;          // :213-222: with use_imu the reference ignores odometry messages
     in.pose_out = static_cast<double *>(d_pose_out);
     in.pose_ss = (long long)T * 3;
     CK(cudaMemsetAsync(g.L.step, 0, sizeof(int), g.stream));
     if (!graphs) continue;
-    int rc = capture_step(h, g, in, g.replay_gs);
+    // The graphs are captured ONCE per group with a descriptor that only points at replay_in_dev; a new set of input
+    // arrays rewrites those 100 bytes on the device, not the graph (no capture / instantiate inside a timed replay).
+    CK(cudaMemcpyAsync(g.replay_in_dev, &in, sizeof(InputRef), cudaMemcpyHostToDevice, g.stream));
+    InputRef via{};
+    via.indirect = g.replay_in_dev;
+    int rc = capture_step(h, g, via, g.replay_gs);
     if (rc) return rc;
   }
   // groups are issued round-robin; each one's stream orders its own steps, nothing orders groups against each other
@@ -764,6 +805,7 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
 
 // ---- accessors --------------------------------------------------------------------------------
 int rekf_sync(rekf_handle *h) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   CK(join_all(h));
   std::vector<SessionState> st(h->L.S);
@@ -777,6 +819,7 @@ int rekf_sync(rekf_handle *h) {
 }
 
 int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, size_t bytes) {
+  DeviceGuard dev_guard(h);
   if (!h || !name || !out) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
   if (session < 0 || session >= L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
@@ -799,6 +842,7 @@ int rekf_debug_copy(rekf_handle *h, int session, const char *name, void *out, si
 }
 
 int rekf_device_error_flags(rekf_handle *h, int session, int *flags_out) {
+  DeviceGuard dev_guard(h);
   if (!h || !flags_out) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -808,6 +852,7 @@ int rekf_device_error_flags(rekf_handle *h, int session, int *flags_out) {
 }
 
 int rekf_dim(rekf_handle *h, int session) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -815,6 +860,7 @@ int rekf_dim(rekf_handle *h, int session) {
 }
 
 int rekf_time(rekf_handle *h, int session, double *time_out) {
+  DeviceGuard dev_guard(h);
   if (!h || !time_out) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -824,6 +870,7 @@ int rekf_time(rekf_handle *h, int session, double *time_out) {
 }
 
 int rekf_get_mu(rekf_handle *h, int session, double *mu, int cap, int *n_out) {
+  DeviceGuard dev_guard(h);
   if (!h || (!mu && cap > 0)) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -840,6 +887,7 @@ int rekf_get_mu(rekf_handle *h, int session, double *mu, int cap, int *n_out) {
 }
 
 int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) {
+  DeviceGuard dev_guard(h);
   if (!h || !pose) return REKF_ERR_BAD_ARGUMENT;
   if (session < 0 || session >= h->L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
   const Layout &L = h->L;
@@ -856,6 +904,7 @@ int rekf_get_pose(rekf_handle *h, int session, double pose[3], double cov33[9]) 
 }
 
 int rekf_batch_get_pose(rekf_handle *h, double *poses) {
+  DeviceGuard dev_guard(h);
   if (!h || !poses) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
   // every group reads its own sessions on its own stream, then the host waits for all of them
@@ -871,6 +920,7 @@ int rekf_batch_get_pose(rekf_handle *h, double *poses) {
 // own step (stream-ordered, no host wait); the ticket is redeemed later.  At most Group::kPoseSlots tickets may be
 // outstanding.
 int rekf_batch_request_poses(rekf_handle *h, int64_t *ticket_out) {
+  DeviceGuard dev_guard(h);
   if (!h || !ticket_out) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
   const int slot = (int)(h->pose_ticket % Group::kPoseSlots);
@@ -884,6 +934,7 @@ int rekf_batch_request_poses(rekf_handle *h, int64_t *ticket_out) {
 }
 
 int rekf_batch_fetch_poses(rekf_handle *h, int64_t ticket, double *poses) {
+  DeviceGuard dev_guard(h);
   if (!h || !poses) return REKF_ERR_BAD_ARGUMENT;
   if (ticket < 0 || ticket >= h->pose_ticket || ticket + Group::kPoseSlots <= h->pose_ticket)
     return fail(h, REKF_ERR_BAD_ARGUMENT, "pose ticket %lld is not outstanding", (long long)ticket);
@@ -896,6 +947,7 @@ int rekf_batch_fetch_poses(rekf_handle *h, int64_t ticket, double *poses) {
 }
 
 int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, int cap, int *count_out) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -913,6 +965,7 @@ int rekf_get_landmarks(rekf_handle *h, int session, double *xy, double *cov2x2, 
 }
 
 int rekf_get_markers(rekf_handle *h, int session, double *markers, int cap, int *count_out) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -928,6 +981,7 @@ int rekf_get_markers(rekf_handle *h, int session, double *markers, int cap, int 
 }
 
 int rekf_get_sigma(rekf_handle *h, int session, double *sigma, int ld) {
+  DeviceGuard dev_guard(h);
   if (!h || !sigma) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -942,8 +996,68 @@ int rekf_get_sigma(rekf_handle *h, int session, double *sigma, int ld) {
   return REKF_OK;
 }
 
+// GetState() (reflector_ekf_slam.h:37-40) in ONE stream synchronisation: time, mu, the full covariance and the sticky
+// device flags.  The caller passes the dimension it expects (its mirror's size); when the state has grown the call
+// returns REKF_ERR_CAPACITY with *n_out set and nothing copied, and the caller resizes and repeats.
+int rekf_get_state(rekf_handle *h, int session, int n_expect, double *time_out, double *mu, double *sigma, int ld, int *n_out, int *flags_out) {
+  DeviceGuard dev_guard(h);
+  if (!h || n_expect < 3 || !mu || (sigma && ld < n_expect)) return REKF_ERR_BAD_ARGUMENT;
+  const Layout &L = h->L;
+  if (session < 0 || session >= L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
+  const size_t n = (size_t)n_expect;
+  int rc = stage_reserve(h, 8 + n + (sigma ? n * n : 0));
+  if (rc) return rc;
+  if (!h->hdr_host) CK(cudaMallocHost(&h->hdr_host, 8 * sizeof(double)));
+  double *hdr = h->stage_dev, *dmu = h->stage_dev + 8, *dsig = sigma ? dmu + n : nullptr;
+  // behind every group's work: the getter's stream waits for the groups instead of the host joining them first
+  for (auto &g : h->groups) {
+    if (g.stream == h->stream) continue;
+    CK(cudaEventRecord(g.done, g.stream));
+    CK(cudaStreamWaitEvent(h->stream, g.done, 0));
+  }
+  k_pack_state<<<dim3((n_expect + 255) / 256, sigma ? n_expect : 1), 256, 0, h->stream>>>(L, session, n_expect, hdr, dmu, dsig);
+  CK(cudaMemcpyAsync(h->hdr_host, hdr, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(mu, dmu, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream));
+  if (sigma)
+    CK(cudaMemcpy2DAsync(sigma, sizeof(double) * ld, dsig, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  const int n_dev = (int)h->hdr_host[0];
+  if (n_out) *n_out = n_dev;
+  if (time_out) *time_out = h->hdr_host[1];
+  if (flags_out) *flags_out = (int)h->hdr_host[2];
+  if (n_dev != n_expect) return fail(h, REKF_ERR_CAPACITY, "state dimension is %d, caller expected %d", n_dev, n_expect);
+  return REKF_OK;
+}
+
+// Page-lock a caller-owned host buffer (the adapter's covariance mirror) so that rekf_get_state / rekf_get_sigma copy into
+// it at PCIe speed instead of through the driver's pageable staging.  Thin wrappers: no CUDA types cross the ABI.
+int rekf_host_register(rekf_handle *h, void *ptr, size_t bytes) {
+  DeviceGuard dev_guard(h);
+  if (!h || !ptr || !bytes) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  return REKF_OK;
+}
+int rekf_host_unregister(rekf_handle *h, void *ptr) {
+  DeviceGuard dev_guard(h);
+  if (!h || !ptr) return REKF_ERR_BAD_ARGUMENT;
+  CK(cudaHostUnregister(ptr));
+  return REKF_OK;
+}
+
+// cumulative counters of one session: {updates, whole frames on the fp64 SYRK, flagged slots done by k_syrk_exact_rows}
+int rekf_get_counters(rekf_handle *h, int session, int64_t out[3]) {
+  DeviceGuard dev_guard(h);
+  if (!h || !out) return REKF_ERR_BAD_ARGUMENT;
+  SessionState st;
+  int rc = read_state(h, session, &st);
+  if (rc) return rc;
+  out[0] = st.n_updates; out[1] = st.n_exact_frames; out[2] = st.n_exact_slots;
+  return REKF_OK;
+}
+
 int rekf_get_match_result(rekf_handle *h, int session, int *state_pairs, int *n_state, int *map_pairs, int *n_map,
                           int *new_ids, int *n_new, int cap) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -962,6 +1076,7 @@ int rekf_get_match_result(rekf_handle *h, int session, int *state_pairs, int *n_
 }
 
 int rekf_predict_state(rekf_handle *h, int session, double time, double *mu, int cap, double *sigma, int ld) {
+  DeviceGuard dev_guard(h);
   if (!h || !mu) return REKF_ERR_BAD_ARGUMENT;
   SessionState st;
   int rc = read_state(h, session, &st);
@@ -980,6 +1095,7 @@ int rekf_predict_state(rekf_handle *h, int session, double time, double *mu, int
 
 // ---- state injection / persistence ----------------------------------------------------------------
 int rekf_set_state(rekf_handle *h, int session, double time, const double vt[3], const double *mu, int n, const double *sigma, int ld) {
+  DeviceGuard dev_guard(h);
   if (!h || !mu || !sigma || n < 3 || ((n - 3) & 1) || ld < n) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
   if (session < 0 || session >= L.S) return fail(h, REKF_ERR_BAD_ARGUMENT, "session %d out of range", session);
@@ -1005,6 +1121,7 @@ int rekf_set_state(rekf_handle *h, int session, double time, const double vt[3],
 }
 
 int rekf_set_map(rekf_handle *h, const float *xy, const double *cov2x2, int count) {
+  DeviceGuard dev_guard(h);
   if (!h || count < 0 || (count > 0 && (!xy || !cov2x2))) return REKF_ERR_BAD_ARGUMENT;
   const Layout &L = h->L;
   if (count > L.mapcap) return fail(h, REKF_ERR_CAPACITY, "%d beacons exceed max_map_landmarks %d", count, L.mapcap);
@@ -1111,12 +1228,14 @@ int rekf_save_map_txt(rekf_handle *h, int session, const char *filebase) {
 
 // ---- timing ---------------------------------------------------------------------------------------
 int rekf_timer_start(rekf_handle *h) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   CK(join_all(h));                                   // the GPU is idle: t0 is stamped now, before any group's work
   CK(cudaEventRecord(h->t0, h->stream));
   return REKF_OK;
 }
 int rekf_timer_stop(rekf_handle *h, float *ms) {
+  DeviceGuard dev_guard(h);
   if (!h || !ms) return REKF_ERR_BAD_ARGUMENT;
   for (auto &g : h->groups) {                        // t1 is stamped after the last group has finished
     CK(cudaEventRecord(g.done, g.stream));
@@ -1128,6 +1247,7 @@ int rekf_timer_stop(rekf_handle *h, float *ms) {
   return REKF_OK;
 }
 int rekf_profile_enable(rekf_handle *h, int enable) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   CK(join_all(h));
   drain_profile(h);
@@ -1140,6 +1260,7 @@ int rekf_profile_enable(rekf_handle *h, int enable) {
   return REKF_OK;
 }
 int rekf_profile_read(rekf_handle *h, const char **names, double *mean_us, int *calls, int cap, int *count_out) {
+  DeviceGuard dev_guard(h);
   if (!h) return REKF_ERR_BAD_ARGUMENT;
   CK(join_all(h));
   drain_profile(h);

@@ -828,6 +828,11 @@ __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in_arg) {
     st.N = N + N2;
     if (overflow) st.flags |= FLAG_LANDMARK_CAPACITY;
     st.ticket = 0;
+    if (st.r > 0) {
+      st.n_updates += 1;
+      if (st.exact_update) st.n_exact_frames += 1;
+      else st.n_exact_slots += min(st.exact_slots, kMaxExactSlots);
+    }
     if (in.pose_out) {
       double *o = in.pose_out + (size_t)s * in.pose_ss + (size_t)t_idx * 3;
       o[0] = mu[0]; o[1] = mu[1]; o[2] = mu[2];
@@ -860,6 +865,18 @@ __global__ void k_pack_mu(Layout L, int s, double *out) {
   const int n_ref = 3 + 2 * L.st[s].N;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_ref) out[i] = L.mu[(size_t)s * L.ld + ref_to_slot(i)];
+}
+// rekf_get_state: header {n_ref, time, flags}, then mu (n_ref) and the full symmetric column-major sigma (n_ref x n_ref), all
+// in one launch; mu / sigma are only written when the caller's idea of the dimension (n_expect) is right
+__global__ void k_pack_state(Layout L, int s, int n_expect, double *hdr, double *out_mu, double *out_sigma) {
+  const SessionState &st = L.st[s];
+  const int n_ref = 3 + 2 * st.N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i == 0 && j == 0) { hdr[0] = (double)n_ref; hdr[1] = st.time; hdr[2] = (double)st.flags; }
+  if (n_ref != n_expect || i >= n_ref || j >= n_ref) return;
+  const double *Sg = L.sigma + (size_t)s * L.ld * L.ld;
+  if (out_sigma) out_sigma[(size_t)j * n_ref + i] = Sg[sym_idx(ref_to_slot(i), ref_to_slot(j), L.ld)];
+  if (j == 0) out_mu[i] = L.mu[(size_t)s * L.ld + ref_to_slot(i)];
 }
 // landmark means and diagonal 2x2 blocks (row-major), what the node reads for markers / saving
 __global__ void k_pack_landmarks(Layout L, int s, double *xy, double *cov) {

@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "rekf_predict_state", "rekf_set_state", "rekf_set_map", "rekf_get_map", "rekf_load_map_txt", "rekf_save_map_txt",
     "rekf_sync", "rekf_stream", "rekf_timer_start", "rekf_timer_stop", "rekf_profile_enable", "rekf_profile_read",
     "rekf_launch_count", "rekf_device_error_flags", "rekf_debug_copy", "rekf_batch_request_poses", "rekf_batch_fetch_poses",
-    "rekf_get_markers", "rekf_batch_handle_step",
+    "rekf_get_markers", "rekf_batch_handle_step", "rekf_get_state", "rekf_host_register", "rekf_host_unregister", "rekf_get_counters",
 ]
 
 
@@ -90,6 +90,10 @@ def load_library(path=None):
         "rekf_batch_fetch_poses": (i, [vp, C.c_int64, vp]),
         "rekf_get_markers": (i, [vp, i, vp, i, P(i)]),
         "rekf_batch_handle_step": (i, [vp, vp, vp, vp, vp, i]),
+        "rekf_get_state": (i, [vp, i, i, P(d), vp, vp, i, P(i), P(i)]),
+        "rekf_host_register": (i, [vp, vp, C.c_size_t]),
+        "rekf_host_unregister": (i, [vp, vp]),
+        "rekf_get_counters": (i, [vp, i, P(C.c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -231,6 +235,22 @@ class EKFBatch:
         out = np.zeros((n, n), order="F")
         self._ck(self.lib.rekf_get_sigma(self.h, s, out.ctypes.data_as(C.c_void_p), n))
         return np.ascontiguousarray(out)
+
+    def state(self, s=0, n_expect=None, with_sigma=True):
+        """(time, mu, sigma, flags) in one synchronisation (rekf_get_state)."""
+        n = self.dim(s) if n_expect is None else n_expect
+        mu = np.zeros(n)
+        sig = np.zeros((n, n), order="F") if with_sigma else None
+        t, nn, fl = C.c_double(), C.c_int(), C.c_int()
+        self._ck(self.lib.rekf_get_state(self.h, s, n, C.byref(t), _ptr(mu), None if sig is None else sig.ctypes.data_as(C.c_void_p), n,
+                                         C.byref(nn), C.byref(fl)))
+        return t.value, mu, (None if sig is None else np.ascontiguousarray(sig)), fl.value
+
+    def counters(self, s=0):
+        """{updates, exact_frames, exact_slots}: how often the int8 covariance update left the tensor path (cumulative)."""
+        out = (C.c_int64 * 3)()
+        self._ck(self.lib.rekf_get_counters(self.h, s, out))
+        return {"updates": out[0], "exact_frames": out[1], "exact_slots": out[2]}
 
     def match_result(self, s=0):
         cap = 1024

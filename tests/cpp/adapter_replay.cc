@@ -2,7 +2,11 @@
 // (reference src/ros_node.cc:627-660, :421-561): one odometry message, one observation, GetState() after
 // each.  Reads a stream dumped by tests/test_cpp_adapter.py, writes the final state for comparison with the
 // oracle.  Usage: adapter_replay <stream.bin> <out.bin>
+// Default: the CI stub of Eigen + the interface (tests/stubs).  -DREKF_ADAPTER_REAL_HEADERS: the reference's own
+// ekf_slam_interface.h / sensor_data.h (from /root/reference/include) over the Eigen stand-in of oracle/shim.
+#ifndef REKF_ADAPTER_REAL_HEADERS
 #define REKF_ADAPTER_STUB_TYPES
+#endif
 #include "reflector_ekf_slam/reflector_ekf_slam_b200.h"
 
 #include <cstdint>
