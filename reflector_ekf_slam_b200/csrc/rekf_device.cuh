@@ -106,7 +106,8 @@ struct Layout {
   double *Sbuf;   // [S][rld][sld] column-major lower triangle of S, then L; row r carries ν → L⁻¹ν
   double *Dinv;   // [S][rld/32][32][32] inverses of L's diagonal blocks
   float *Wt_hi, *Wt_lo;  // [S][ld][rld] tf32 hi/lo split of Wᵀ (K-major operands of the tcgen05 SYRK)
-  double *W64;    // [S][ld][rld] fp64 Wᵀ (REKF_COV_SIMT_F64 only, else nullptr)
+  double *W64;    // [S][rld][ld] fp64 W, measurement-row major: row k holds W[k][all slots] (fp64 SYRK and the exact rows; nullptr in tf32 mode)
+  double *Ybuf;   // [S][rld][ld] Y = H·Σ, written by k_gather_y beside the Cholesky, read by k_solve_w3 as coalesced tiles
   int8_t *Wq;     // [S][4][kq/64][ld][64] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4), K in
                   // 64-byte chunks OUTSIDE the row index: a TMA box of 128 rows x 64 K-bytes is one contiguous 8 KB block
   int *Wexp;      // [S][ld] per-row power-of-two exponent e_c of Wq

@@ -28,8 +28,8 @@ using namespace rekf;
 
 namespace {
 
-enum KernelId { K_ODOM = 0, K_FRONT, K_INNOV, K_CHOL, K_SOLVE, K_SYRK_EXACT, K_SYRK, K_AUGMENT, K_COUNT };
-const char *kKernelNames[K_COUNT] = {"k_odometry", "k_observation_front", "k_innovation", "k_cholesky",
+enum KernelId { K_ODOM = 0, K_FRONT, K_GATHER, K_INNOV, K_CHOL, K_SOLVE, K_SYRK_EXACT, K_SYRK, K_AUGMENT, K_COUNT };
+const char *kKernelNames[K_COUNT] = {"k_odometry", "k_observation_front", "k_gather_y(side stream)", "k_innovation", "k_cholesky",
                                      "k_solve_w", "k_syrk_exact_rows", "k_syrk", "k_augment"};
 
 struct ProfRecord { int id; cudaEvent_t a, b; };
@@ -44,6 +44,8 @@ struct Group {
   cudaStream_t stream = nullptr;       // where this group's work is issued (the handle's main stream while profiling)
   cudaStream_t home_stream = nullptr;  // the group's own stream
   bool own_stream = false;
+  cudaStream_t side_stream = nullptr;  // parallel branch of the step: Y = H·Σ beside innovation + Cholesky
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Layout L{};
   // device mailbox for host-delivered messages of this group's sessions + pinned staging ring
   char *mb_dev = nullptr;
@@ -207,7 +209,7 @@ inline cudaError_t join_all(rekf_handle *h) {
     cudaError_t e = cudaStreamSynchronize(g.home_stream);
     if (e != cudaSuccess) return e;
   }
-  return cudaStreamSynchronize(h->stream);
+  return cudaStreamSynchronize(h->stream);   // side branches are joined back into these streams inside every step
 }
 
 void drain_profile(rekf_handle *h) {
@@ -223,7 +225,10 @@ void drain_profile(rekf_handle *h) {
   h->prof.clear();
 }
 
-size_t smem_front(const Layout &L) { return sizeof(int) * 2 * (size_t)L.mcap + sizeof(float2) * (size_t)L.Ncap; }
+// kind / target lists, float32 + fp64 landmark means, the frame's observations
+size_t smem_front(const Layout &L) {
+  return sizeof(int) * 2 * (size_t)L.mcap + sizeof(float2) * (size_t)L.Ncap + sizeof(double2) * (size_t)L.Ncap + sizeof(float2) * (size_t)L.mcap + 32;
+}
 size_t smem_chol(const Layout &L) { return sizeof(double) * ((size_t)(L.rcap + 1) * kPS + (size_t)kCholNb * kPS); }
 size_t smem_solve(const Layout &L) { return sizeof(double) * (size_t)L.rld * kYS; }
 
@@ -262,6 +267,16 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     ProfScope p(h, K_FRONT, stream);
     k_observation_front<<<L.Sg, 1024, smem_front(L), stream>>>(L, in);
   }
+  if (h->solve_w2) {
+    // fork: Y = H·Σ needs only the match lists and the predicted Σ — a parallel branch (under capture: of the step graph)
+    CK(cudaEventRecord(grp.ev_fork, stream));
+    CK(cudaStreamWaitEvent(grp.side_stream, grp.ev_fork, 0));
+    {
+      ProfScope p(h, K_GATHER, grp.side_stream);
+      k_gather_y<<<dim3(L.ld / 128, (L.rcap / 2 + kGYPairs - 1) / kGYPairs, L.Sg), 256, 0, grp.side_stream>>>(L);
+    }
+    CK(cudaEventRecord(grp.ev_join, grp.side_stream));
+  }
   {
     ProfScope p(h, K_INNOV, stream);
     const int g = (L.rcap + 15) / 16;
@@ -272,6 +287,7 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     if (h->chol_resident) k_cholesky_smem<<<L.Sg, kCholSmemThreads, smem_chol_resident(L.rcap), stream>>>(L);
     else k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
   }
+  if (h->solve_w2) CK(cudaStreamWaitEvent(stream, grp.ev_join, 0));   // join before the TRSM
   CK(cudaGetLastError());
   return 0;
 }
@@ -417,6 +433,9 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   for (int i = 0; i < Group::kSlots; ++i) CK(cudaEventCreateWithFlags(&g.slot_done[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.phase_ev, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost(&g.pose_host, sizeof(double) * 3 * S * Group::kPoseSlots));
   for (int i = 0; i < Group::kPoseSlots; ++i) CK(cudaEventCreateWithFlags(&g.pose_done[i], cudaEventDisableTiming));
   // kernels index every input by the absolute session: bias the bases by -s0 strides
@@ -444,6 +463,9 @@ void destroy_group(Group &g) {
     if (gs->wide) cudaGraphExecDestroy(gs->wide);
   }
   if (g.phase_ev) cudaEventDestroy(g.phase_ev);
+  if (g.ev_fork) cudaEventDestroy(g.ev_fork);
+  if (g.ev_join) cudaEventDestroy(g.ev_join);
+  if (g.side_stream) cudaStreamDestroy(g.side_stream);
   if (g.mb_host) cudaFreeHost(g.mb_host);
   if (g.pose_host) cudaFreeHost(g.pose_host);
   for (auto &e : g.slot_done) if (e) cudaEventDestroy(e);
@@ -556,6 +578,7 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   if ((rc = dev_alloc(h, &L.Qd, S * L.rcap))) return rc;
   if ((rc = dev_alloc(h, &L.Sbuf, S * L.rld * L.sld))) return rc;
   if ((rc = dev_alloc(h, &L.Dinv, S * (L.rld / kCholNb) * kCholNb * kCholNb))) return rc;
+  if ((rc = dev_alloc(h, &L.Ybuf, S * L.rld * L.ld))) return rc;
   if (opts->cov_update == REKF_COV_SIMT_F64) {
     if ((rc = dev_alloc(h, &L.W64, S * L.ld * L.rld))) return rc;
   } else if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {

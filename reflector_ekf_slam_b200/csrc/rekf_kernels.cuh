@@ -159,46 +159,167 @@ __device__ inline void warp_argmin(double &d, int &j) {
 
 constexpr int kMatchNew = 0, kMatchState = 1, kMatchMap = 2;
 
+// One predict of the 3x3 pose block and the pose itself (thread 0): P ← G3·P·G3ᵀ + V, μ[0:3] += d, θ wrapped.
+__device__ inline void predict_pose_block(const MotionTerms &t, double P[9], double pose[3]) {
+  double T[9];
+  for (int j = 0; j < 3; ++j) {          // T = G3·P (rows), P' = T·G3ᵀ (columns)
+    T[0 + j] = P[0 + j] + t.g02 * P[6 + j];
+    T[3 + j] = P[3 + j] + t.g12 * P[6 + j];
+    T[6 + j] = P[6 + j];
+  }
+  for (int i = 0; i < 3; ++i) {
+    P[i * 3 + 0] = T[i * 3 + 0] + t.g02 * T[i * 3 + 2];
+    P[i * 3 + 1] = T[i * 3 + 1] + t.g12 * T[i * 3 + 2];
+    P[i * 3 + 2] = T[i * 3 + 2];
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = i; j < 3; ++j) {
+      const double v = P[i * 3 + j] + t.V[i * 3 + j];
+      P[i * 3 + j] = v;
+      P[j * 3 + i] = v;
+    }
+  pose[0] += t.d[0];
+  pose[1] += t.d[1];
+  pose[2] = wrap_angle(pose[2] + t.d[2]);
+}
+
+// The kernel is latency-bound (one CTA per session, a few KB of traffic), so it is organised around its dependent global
+// round trips: everything that does not depend on the message — rows 0..2 of Σ, the landmark means — is requested by
+// all threads at entry; meanwhile thread 0 walks the only serial chain (input descriptor → step counter → message →
+// both motion models → 3x3 block and pose) and warp 1 stages the frame's observations.  After ONE barrier every thread
+// applies both predicts to its columns from registers (the two updates in the reference's order, so no sum changes), and
+// association, compaction (ballot + popc prefix) and the measurement rows run out of shared memory.
+struct FrontShared {
+  double g[4];            // g02, g12 of the odometry predict (0 when there is none), g02, g12 of the observation predict
+  double pose[3];         // pose after both predicts
+  double sn, cs;
+  double time;            // observation stamp
+  int n, N, m, flags0, has_odom, t_idx;
+  const float *xy;
+  const double *gps;
+  int counts[3];
+};
+
 __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in_arg) {
   timeline_mark(L, 1);
-  const InputRef in = resolve_input(in_arg);
   extern __shared__ int sm_i[];
+  __shared__ FrontShared fs;
   const int s = L.s0 + blockIdx.x;
-  if (in.fuse_odom) odometry_cta(L, s, in);        // replay: this step's HandleOdometryMessage first
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int ld = L.ld;
   SessionState &st = L.st[s];
-  const int t_idx = current_step(in);
-  const double time = in.obs_time[(size_t)s * in.time_ss + t_idx];
-  const float *xy = in.obs_xy + (size_t)s * in.xy_ss + (size_t)t_idx * in.m_stride * 2;
-  int m = in.obs_count ? in.obs_count[s] : in.m_fixed;
-  const double t_state = st.time;
-  const int flags0 = st.flags;
-  __syncthreads();
-  predict_cta(L, s, time - t_state);               // :232-233, no sign check on dt
-  int flag_add = 0;
-  if (m > L.mcap) { m = L.mcap; flag_add |= FLAG_OBS_CAPACITY; }
-  if (m < 0) m = 0;
-
+  double *mu = L.mu + (size_t)s * ld;
+  double *Sg = L.sigma + (size_t)s * ld * ld;
   int *kind = sm_i;                 // [mcap]
   int *target = sm_i + L.mcap;      // [mcap]
-  // landmark means rounded to float32 once per frame (:431 does it per pair; F2F.F32.F64 is a slow-pipe op)
-  float2 *lmf = reinterpret_cast<float2 *>(sm_i + 2 * L.mcap);   // [Ncap]
-  const double *mu = L.mu + (size_t)s * L.ld;
-  const int N = st.N;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+  // landmark means: float32 once per frame (:431 rounds per pair; F2F.F32.F64 is a slow-pipe op) and the doubles for the rows
+  float2 *lmf = reinterpret_cast<float2 *>(sm_i + 2 * L.mcap);                    // [Ncap]
+  double2 *lmd = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(lmf + L.Ncap) + 15) & ~(uintptr_t)15);   // [Ncap], 16-byte aligned
+  float2 *xys = reinterpret_cast<float2 *>(lmd + L.Ncap);                          // [mcap] this frame's observations
+
+  // ---- requests that do not depend on the message ------------------------------------------------------------
+  constexpr int kPre = 2;           // columns per thread held in registers (covers Ncap <= 1022; the rest goes through a loop)
+  double r0[kPre], r1[kPre], r2[kPre];
+#pragma unroll
+  for (int u = 0; u < kPre; ++u) {
+    const int c = kPoseSlots + tid + u * 1024;
+    r0[u] = r1[u] = r2[u] = 0.0;
+    if (c < L.ncap) { r0[u] = Sg[c]; r1[u] = Sg[(size_t)ld + c]; r2[u] = Sg[(size_t)2 * ld + c]; }
+  }
+  for (int j = tid; j < L.Ncap; j += blockDim.x) {          // slots past the live N hold zeros: harmless
     const double2 l = *reinterpret_cast<const double2 *>(mu + kPoseSlots + 2 * j);
+    lmd[j] = l;
     lmf[j] = make_float2((float)l.x, (float)l.y);
   }
-  __syncthreads();
+
+  // ---- the serial chain (thread 0) and the observation staging (warp 1) ----------------------------------------
+  if (tid == 0) {
+    const InputRef in = resolve_input(in_arg);
+    const int t_idx = current_step(in);
+    const double *msg = in.odom ? in.odom + (size_t)s * in.odom_ss + (size_t)t_idx * 4 : nullptr;
+    const double t_obs = in.obs_time[(size_t)s * in.time_ss + t_idx];
+    int m = in.obs_count ? in.obs_count[s] : in.m_fixed;
+    double t_state = st.time;
+    double vt[3] = {st.vt[0], st.vt[1], st.vt[2]};
+    double pose[3] = {mu[0], mu[1], mu[2]};
+    double P[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) P[i * 3 + j] = Sg[sym_idx(i, j, ld)];
+    const int N = st.N;
+    fs.flags0 = st.flags;
+    fs.g[0] = fs.g[1] = 0.0;
+    fs.has_odom = 0;
+    if (in.fuse_odom) {                            // replay / step call: this step's HandleOdometryMessage first (:208-223)
+      const double t_od = msg[0];
+      if (!(t_od < t_state)) {                     // :211 stale messages are dropped
+        vt[0] = msg[1]; vt[1] = msg[2]; vt[2] = msg[3];      // :216 latched BEFORE predicting
+        const MotionTerms t = motion_model(L, vt, pose[2], t_od - t_state);
+        fs.g[0] = t.g02; fs.g[1] = t.g12;
+        fs.has_odom = 1;
+        predict_pose_block(t, P, pose);
+        t_state = t_od;
+        st.vt[0] = vt[0]; st.vt[1] = vt[1]; st.vt[2] = vt[2];
+      }
+    }
+    const MotionTerms t = motion_model(L, vt, pose[2], t_obs - t_state);   // :232-233, no sign check on dt
+    fs.g[2] = t.g02; fs.g[3] = t.g12;
+    predict_pose_block(t, P, pose);
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) Sg[(size_t)i * ld + j] = P[i * 3 + j];
+    mu[0] = pose[0]; mu[1] = pose[1]; mu[2] = pose[2];
+    fs.pose[0] = pose[0]; fs.pose[1] = pose[1]; fs.pose[2] = pose[2];
+    sincos(pose[2], &fs.sn, &fs.cs);
+    int flag_add = 0;
+    if (m > L.mcap) { m = L.mcap; flag_add |= FLAG_OBS_CAPACITY; }
+    if (m < 0) m = 0;
+    fs.flags0 |= flag_add;
+    fs.time = t_obs; fs.N = N; fs.n = internal_dim(N); fs.m = m; fs.t_idx = t_idx;
+    fs.gps = in.gps ? in.gps + 4 * s : nullptr;
+    fs.counts[0] = fs.counts[1] = fs.counts[2] = 0;
+  } else if (warp == 1) {
+    const InputRef in = resolve_input(in_arg);
+    const int t_idx = current_step(in);
+    const float *xy = in.obs_xy + (size_t)s * in.xy_ss + (size_t)t_idx * in.m_stride * 2;
+    int m = in.obs_count ? in.obs_count[s] : in.m_fixed;
+    m = max(0, min(m, L.mcap));
+    for (int i = lane; i < m; i += 32) xys[i] = *reinterpret_cast<const float2 *>(xy + 2 * i);
+    if (lane == 0) fs.xy = xy;
+  }
   const int Mmap = *L.map_count;
-  const double px = mu[0], py = mu[1], th = mu[2];
-  double sn, cs;
-  sincos(th, &sn, &cs);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  __syncthreads();
+
+  // ---- both predicts on rows 0 and 1 (the mirrored columns are not stored) ---------------------------------------
+  const int n = fs.n, N = fs.N, m = fs.m;
+  {
+    const double ga0 = fs.g[0], ga1 = fs.g[1], gb0 = fs.g[2], gb1 = fs.g[3];
+    const bool has_odom = fs.has_odom != 0;
+#pragma unroll
+    for (int u = 0; u < kPre; ++u) {
+      const int c = kPoseSlots + tid + u * 1024;
+      if (c < n) {
+        double v0 = r0[u], v1 = r1[u];
+        if (has_odom) { v0 += ga0 * r2[u]; v1 += ga1 * r2[u]; }
+        v0 += gb0 * r2[u]; v1 += gb1 * r2[u];
+        Sg[c] = v0;
+        Sg[(size_t)ld + c] = v1;
+      }
+    }
+    for (int c = kPoseSlots + tid + kPre * 1024; c < n; c += blockDim.x) {
+      const double s2 = Sg[(size_t)2 * ld + c];
+      double v0 = Sg[c], v1 = Sg[(size_t)ld + c];
+      if (has_odom) { v0 += ga0 * s2; v1 += ga1 * s2; }
+      v0 += gb0 * s2; v1 += gb1 * s2;
+      Sg[c] = v0;
+      Sg[(size_t)ld + c] = v1;
+    }
+  }
+  const double px = fs.pose[0], py = fs.pose[1], th = fs.pose[2], sn = fs.sn, cs = fs.cs;
 
   // --- ReflectorMatch: one warp per observation, lanes stride over landmarks -------------------
   for (int i = warp; i < m; i += nwarps) {
     // point_transformed_to_global_frame (:389-393): double arithmetic, float32 result
-    const double ox = (double)xy[2 * i], oy = (double)xy[2 * i + 1];
+    const float2 o = xys[i];
+    const double ox = (double)o.x, oy = (double)o.y;
     const float gx = (float)(ox * cs - oy * sn + px);
     const float gy = (float)(ox * sn + oy * cs + py);
     int k = kMatchNew, tgt = -1;
@@ -219,14 +340,18 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     if (k == kMatchNew && N > 0) {                 // :426-451
       double best = INFINITY;
       int bj = 0x7fffffff;
-      // Compare squared distances (dx², dy² are exact in fp64, so d² orders exactly like the reference's
-      // sqrt(d²) except where two sqrt results round to the same double); sqrt only for the gate.
+      // The reference takes the nearest landmark and then asks whether it is within 0.6 m (:446), so only landmarks inside the
+      // gate can matter: an fp32 estimate of d² (two FP32 ops per pair) screens the N candidates with a margin far above its
+      // rounding error, and the exact comparison — the float differences widened to fp64, d² exact there, lowest index on
+      // ties — runs on the one or two survivors.  (Widening every pair cost two quarter-rate F2F per pair: 2·10^5 per frame.)
       for (int j = lane; j < N; j += 32) {
         const float2 l = lmf[j];
         const float dfx = gx - l.x, dfy = gy - l.y;                                // :431, :433
-        const double dx = (double)dfx, dy = (double)dfy;
-        const double d2 = dx * dx + dy * dy;                                       // :437 Euclidean
-        if (d2 < best) { best = d2; bj = j; }
+        if (fmaf(dfx, dfx, dfy * dfy) < 0.3601f) {
+          const double dx = (double)dfx, dy = (double)dfy;
+          const double d2 = dx * dx + dy * dy;                                     // :437 Euclidean
+          if (d2 < best) { best = d2; bj = j; }
+        }
       }
       warp_argmin(best, bj);
       if (sqrt(best) < 0.6) { k = kMatchState; tgt = bj; }                         // :446
@@ -235,26 +360,32 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   }
   __syncthreads();
 
-  // --- ordered compaction: lists keep observation order like the push_backs at :422/:448/:452 --
+  // --- ordered compaction: lists keep observation order like the push_backs at :422/:448/:452.  One warp per list kind:
+  //     ballot over 32 observations at a time, position = running count + popc of the lower lanes ----------------------
   int *sp = L.state_pairs + (size_t)s * L.mcap * 2;
   int *mp = L.map_pairs + (size_t)s * L.mcap * 2;
   int *nw = L.new_ids + (size_t)s * L.mcap;
-  __shared__ int counts[3];
-  if (threadIdx.x < 3) counts[threadIdx.x] = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const int k = kind[i];
-    int pos = 0;
-    for (int u = 0; u < i; ++u) pos += (kind[u] == k);
-    if (k == kMatchState) { sp[2 * pos] = i; sp[2 * pos + 1] = target[i]; }
-    else if (k == kMatchMap) { mp[2 * pos] = i; mp[2 * pos + 1] = target[i]; }
-    else nw[pos] = i;
-    atomicAdd(&counts[k], 1);
+  if (warp < 3) {
+    const int mine = warp;                         // kMatchNew = 0, kMatchState = 1, kMatchMap = 2
+    int run = 0;
+    for (int base = 0; base < m; base += 32) {
+      const int i = base + lane;
+      const bool hit = i < m && kind[i] == mine;
+      const unsigned bal = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = run + __popc(bal & ((1u << lane) - 1u));
+        if (mine == kMatchState) { sp[2 * pos] = i; sp[2 * pos + 1] = target[i]; }
+        else if (mine == kMatchMap) { mp[2 * pos] = i; mp[2 * pos + 1] = target[i]; }
+        else nw[pos] = i;
+      }
+      run += __popc(bal);
+    }
+    if (lane == 0) fs.counts[mine] = run;
   }
   __syncthreads();
-  const int M = counts[kMatchState], Mm = counts[kMatchMap], N2 = counts[kMatchNew];
+  const int M = fs.counts[kMatchState], Mm = fs.counts[kMatchMap], N2 = fs.counts[kMatchNew];
   const int MM = M + Mm;
-  const double *gps = in.gps ? in.gps + 4 * s : nullptr;
+  const double *gps = fs.gps;
   const bool has_gps = gps && gps[0] != 0.0 && MM > 0;   // the GPS rows live inside `if (MM > 0)` (gps.cc:246,305)
   const int r = MM > 0 ? 2 * MM + (has_gps ? 3 : 0) : 0;
 
@@ -271,7 +402,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
       i = sp[2 * k];
       const int j = sp[2 * k + 1];
       slot = kPoseSlots + 2 * j;
-      lx = mu[slot]; ly = mu[slot + 1];
+      lx = lmd[j].x; ly = lmd[j].y;
     } else {                                       // beacon read as float32 (:281-283), no B block (:300)
       i = mp[2 * (k - M)];
       const int j = mp[2 * (k - M) + 1];
@@ -287,8 +418,8 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     Hl[4 * k + 0] = cs;  Hl[4 * k + 1] = sn;
     Hl[4 * k + 2] = -sn; Hl[4 * k + 3] = cs;
     Hslot[2 * k] = slot; Hslot[2 * k + 1] = slot;
-    innov[2 * k] = (double)xy[2 * i] - zh0;
-    innov[2 * k + 1] = (double)xy[2 * i + 1] - zh1;
+    innov[2 * k] = (double)xys[i].x - zh0;
+    innov[2 * k + 1] = (double)xys[i].y - zh1;
     Qd[2 * k] = L.q_obs; Qd[2 * k + 1] = L.q_obs;
   }
   if (has_gps && threadIdx.x < 3) {                // reflector_ekf_slam_gps.cc:314-334
@@ -314,9 +445,9 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     }
   }
   if (threadIdx.x == 0) {
-    st.time = time;                                // :234
+    st.time = fs.time;                             // :234
     st.m = m; st.M = M; st.Mmap = Mm; st.N2 = N2; st.r = r;
-    st.flags = flags0 | flag_add;
+    st.flags = fs.flags0;
     st.ticket = 0;
     st.exact_update = 0;
     st.exact_slots = 0;
@@ -356,6 +487,75 @@ __global__ void __launch_bounds__(256) k_innovation(Layout L) {
   double *Sb = L.Sbuf + (size_t)s * L.rld * L.sld;
   Sb[(size_t)p * L.sld + q] = acc;
   if (p == 0) Sb[(size_t)q * L.sld + r] = L.innov[(size_t)s * L.rcap + q];   // ν as row r: Cholesky turns it into L⁻¹ν
+}
+
+// ---------------------------------------------------------------------------------------------
+// Y = H·Σ (r x n) into global memory, off the critical path: it only needs the match lists and the predicted Σ, so it runs on a
+// side stream (a parallel branch of the step graph) beside k_innovation and the Cholesky, and k_solve_w3 starts from coalesced
+// 256-byte rows instead of gathering.  H has <= 5 non-zeros per row (:272-275): Y[q][c] = A_q·Σ[0:3][c] + B_q·Σ[slot:slot+2][c].
+// Only the upper triangle of Σ is stored: Σ[slot][c] with slot < c is row `slot` (coalesced across the lanes' columns); for
+// columns left of the slot it is Σ[c][slot..slot+1], ONE 16-byte read per lane for both rows of the reflector.
+// grid (ld/128, ceil(rcap/2/16), Sg) x 256 threads: lane = column (4 per lane), warps stride 16 row pairs.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGYPairs = 16;
+__global__ void __launch_bounds__(256) k_gather_y(Layout L) {
+  timeline_mark(L, 3);
+  const int s = L.s0 + blockIdx.z;
+  const SessionState &st = L.st[s];
+  const int r = st.r;
+  const int pair0 = blockIdx.y * kGYPairs;
+  if (r == 0 || 2 * pair0 >= r) return;
+  const int n = internal_dim(st.N);
+  const int ld = L.ld;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double *Sg = L.sigma + (size_t)s * ld * ld;
+  const double *Hp = L.Hp + (size_t)s * L.rcap * 4;
+  const double *Hl = L.Hl + (size_t)s * L.rcap * 2;
+  const int *Hslot = L.Hslot + (size_t)s * L.rcap;
+  double *Y = L.Ybuf + (size_t)s * L.rld * ld;
+  const int cbase = blockIdx.x * 128;
+  if (cbase >= round_up(n, kSigmaTile)) return;
+  double p0[4], p1[4], p2[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int c = cbase + 32 * u + lane;
+    p0[u] = Sg[sym_idx(0, c, ld)]; p1[u] = Sg[sym_idx(1, c, ld)]; p2[u] = Sg[sym_idx(2, c, ld)];
+  }
+  for (int pb = pair0 + warp; pb < pair0 + kGYPairs && 2 * pb < r; pb += 8) {
+    const int q0 = 2 * pb, q1 = q0 + 1;
+    const bool two = q1 < r;
+    const int slot0 = Hslot[q0], slot1 = two ? Hslot[q1] : -1;
+    double xa[4], xb[4], za[4], zb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = cbase + 32 * u + lane;
+      xa[u] = xb[u] = za[u] = zb[u] = 0.0;
+      if (slot0 >= 0) {
+        if (slot0 > c) { const double2 v = *reinterpret_cast<const double2 *>(Sg + (size_t)c * ld + slot0); xa[u] = v.x; xb[u] = v.y; }
+        else { xa[u] = Sg[(size_t)slot0 * ld + c]; xb[u] = Sg[sym_idx(slot0 + 1, c, ld)]; }
+      }
+      if (slot1 == slot0) { za[u] = xa[u]; zb[u] = xb[u]; }
+      else if (slot1 >= 0) {                       // never the case for the reference's row layout; kept general
+        za[u] = Sg[sym_idx(slot1, c, ld)]; zb[u] = Sg[sym_idx(slot1 + 1, c, ld)];
+      }
+    }
+    const double a0 = Hp[4 * q0], a1 = Hp[4 * q0 + 1], a2 = Hp[4 * q0 + 2], l0 = Hl[2 * q0], l1 = Hl[2 * q0 + 1];
+    double b0 = 0, b1 = 0, b2 = 0, m0 = 0, m1 = 0;
+    if (two) { b0 = Hp[4 * q1]; b1 = Hp[4 * q1 + 1]; b2 = Hp[4 * q1 + 2]; m0 = Hl[2 * q1]; m1 = Hl[2 * q1 + 1]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = cbase + 32 * u + lane;
+      const bool live = c < n;
+      double y0 = a0 * p0[u] + a1 * p1[u] + a2 * p2[u];
+      if (slot0 >= 0) y0 += l0 * xa[u] + l1 * xb[u];
+      Y[(size_t)q0 * ld + c] = live ? y0 : 0.0;
+      if (two) {
+        double y1 = b0 * p0[u] + b1 * p1[u] + b2 * p2[u];
+        if (slot1 >= 0) y1 += m0 * za[u] + m1 * zb[u];
+        Y[(size_t)q1 * ld + c] = live ? y1 : 0.0;
+      }
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -613,8 +813,8 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
   if (L.W64) {
     double *W = L.W64 + (size_t)s * ld * rld;
     for (int e = tid; e < kWCols * rld; e += blockDim.x) {
-      const int cc = e / rld, k = e - cc * rld;
-      W[(size_t)(c0 + cc) * rld + k] = (k < r) ? Y[k * kYS + cc] : 0.0;
+      const int k = e / kWCols, cc = e - k * kWCols;
+      W[(size_t)k * ld + c0 + cc] = (k < r) ? Y[k * kYS + cc] : 0.0;
     }
   }
   if (L.Wq) {
@@ -714,9 +914,9 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
   for (int k0 = 0; k0 < r; k0 += 16) {
     for (int e = threadIdx.x; e < 64 * 16; e += 256) {
-      const int row = e >> 4, kk = e & 15;
-      As[kk][row] = W[(size_t)(i0 + row) * rld + k0 + kk];   // rld is zero-padded past r
-      Bs[kk][row] = W[(size_t)(j0 + row) * rld + k0 + kk];
+      const int kk = e >> 6, row = e & 63;                   // measurement-row major panel: coalesced along the slots
+      As[kk][row] = W[(size_t)(k0 + kk) * ld + i0 + row];    // rows past r are zero
+      Bs[kk][row] = W[(size_t)(k0 + kk) * ld + j0 + row];
     }
     __syncthreads();
 #pragma unroll

@@ -4,8 +4,8 @@
 // never has to be formed: W = L⁻¹·H·Σ gives K·ν = Wᵀ·(L⁻¹ν) and K·H·Σ = Wᵀ·W.
 //
 // One CTA = 32 columns of W (32 state slots), 256 threads = 8 warps:
-//   gather   Y[q][c] = Σ_b H[q][b]·Σ[b][c]: H has <= 5 non-zeros per row (:272-275), so each entry is a
-//            16-byte read from row c of the (symmetric) Σ — H·Σ never touches HBM as a matrix;
+//   load     the CTA's 32 columns of Y = H·Σ (k_gather_y computed it on a side stream beside the Cholesky: H has <= 5
+//            non-zeros per row, :272-275, so Y is a block gather of Σ, 3.6 MB per session that stay in L2);
 //   solve    blocked forward substitution, right-looking, 32-row blocks, entirely on the fp64 tensor pipe
 //            (mma.sync m8n8k4 → DMMA, full rate on B200): W_J = X_J·Y_J with the block inverses X_J = L_JJ⁻¹
 //            the Cholesky kernel emits (no substitution chain), then Y_I −= L_IJ·W_J for the rows below with
@@ -44,9 +44,6 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   const int ld = L.ld, sld = L.sld, rld = L.rld;
   const double *Sg = L.sigma + (size_t)s * ld * ld;
   const double *Sb = L.Sbuf + (size_t)s * rld * sld;
-  const double *Hp = L.Hp + (size_t)s * L.rcap * 4;
-  const double *Hl = L.Hl + (size_t)s * L.rcap * 2;
-  const int *Hslot = L.Hslot + (size_t)s * L.rcap;
   double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
   double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [2][64][32] swizzled chunks of an L panel (double buffer)
   double *Xs = Lp + 2 * 32 * kW3LP;                   // [32][32] swizzled inverse of the current diagonal block
@@ -73,75 +70,20 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
 #endif
   REKF_WSTAMP();
 
-  // ---- gather ----------------------------------------------------------------------------------------
-  // The measurement-row descriptors go to shared memory first (one coalesced round trip), so that the only
-  // dependent global access left is the 16-byte read of Σ — and those are issued 2 columns x 8 rows deep.
+  // ---- Y tile: rows 0..r-1 of Y = H·Σ (k_gather_y wrote them beside the Cholesky), this CTA's 32 columns = 256 contiguous
+  //      bytes per row, 16-byte cp.async; rows r..r32-1 of the tile are zero --------------------------------------------
   {
-    double *sh = Lp;                                  // [rcap][6]: h0 h1 h2 l0 l1 slot (aliases the L chunk buffers)
-    for (int q = tid; q < r; q += 256) {
-      sh[6 * q + 0] = Hp[4 * q]; sh[6 * q + 1] = Hp[4 * q + 1]; sh[6 * q + 2] = Hp[4 * q + 2];
-      sh[6 * q + 3] = Hl[2 * q]; sh[6 * q + 4] = Hl[2 * q + 1];
-      sh[6 * q + 5] = (double)Hslot[q];
-    }
-    __syncthreads();
-    REKF_WSTAMP2();
-    // lane = column (its pose entries stay in registers), warps stride the measurement rows: the row descriptor is one
-    // broadcast read, the Y store is conflict free, 28 Σ reads are in flight per lane.
-    // Only the upper triangle of Σ is stored.  Σ[slot][c] with slot < c is row `slot`, columns c0..c0+31: a coalesced
-    // 256-byte segment per warp.  Slots to the right of this CTA's columns (slot > c) are read as Σ[c][slot..slot+1]:
-    // ONE 16-byte read per lane covers both rows of the reflector (a full 32-byte sector for 16 useful bytes — the price
-    // of never writing the lower triangle, paid on ~half of 3.4 MB per session-step).
-    const int c = c0 + lane;
-    const bool live = c < n;
-    const int cl = min(c, ld - 1);
-    const double p0 = Sg[sym_idx(0, cl, ld)], p1 = Sg[sym_idx(1, cl, ld)], p2 = Sg[sym_idx(2, cl, ld)];
-    auto sig_pair = [&](int slot, double &xa, double &xb) {     // Σ[slot][c], Σ[slot+1][c]; slot is even, >= 4
-      if (slot > cl) {
-        const double2 v = *reinterpret_cast<const double2 *>(Sg + (size_t)cl * ld + slot);
-        xa = v.x; xb = v.y;
+    const double *Yg = L.Ybuf + (size_t)s * rld * ld + c0;
+    for (int e = tid; e < r32 * 16; e += 256) {
+      const int q = e >> 4, cc = (e & 15) * 2;
+      double *dst = Y + q * kW3YS + cc;
+      if (q < r) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(Yg + (size_t)q * ld + cc) : "memory");
       } else {
-        xa = Sg[(size_t)slot * ld + cl];
-        xb = Sg[sym_idx(slot + 1, cl, ld)];
-      }
-    };
-    // The two measurement rows of one reflector (rows 2k, 2k+1: :272-275) read the same two rows of Σ, so the gather
-    // walks row PAIRS: 28 Σ reads in flight per lane cover r = 224 in a single latency round (the L1 left beside two
-    // 111 KB CTAs is a few KB: a repeated read is another trip to L2).
-    constexpr int kIt = 14;
-    for (int pb = warp; 2 * pb < r32; pb += 8 * kIt) {
-      double va[kIt], vb[kIt];
-#pragma unroll
-      for (int it = 0; it < kIt; ++it) {
-        const int q = 2 * (pb + 8 * it);
-        const int slot = (q < r) ? (int)sh[6 * q + 5] : -1;
-        va[it] = vb[it] = 0.0;
-        if (slot >= 0) sig_pair(slot, va[it], vb[it]);
-      }
-#pragma unroll
-      for (int it = 0; it < kIt; ++it) {
-        const int q0 = 2 * (pb + 8 * it);
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int q = q0 + e;
-          if (q < r32) {
-            double y = 0.0;
-            if (q < r && live) {
-              const double *h = sh + 6 * q;
-              y = h[0] * p0 + h[1] * p1 + h[2] * p2;
-              const int slot = (int)h[5];
-              if (slot >= 0) {
-                double xa = va[it], xb = vb[it];
-                if (e == 1 && slot != (int)sh[6 * q0 + 5]) sig_pair(slot, xa, xb);   // never the case for the reference's row layout; kept general
-                y += h[3] * xa + h[4] * xb;
-              }
-            }
-            Y[q * kW3YS + lane] = y;
-          }
-        }
+        dst[0] = 0.0; dst[1] = 0.0;
       }
     }
-    REKF_WSTAMP2();
-    __syncthreads();                                  // sh (aliasing Lp) is dead from here on
+    asm volatile("cp.async.commit_group;" ::: "memory");   // waited for together with the first L / X stage below
   }
   REKF_WSTAMP();
 
@@ -323,11 +265,10 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
 
   // ---- operand panels of Wᵀ (row c, K contiguous), zero beyond r ---------------------------------------------------
   if (L.W64) {
-    // 8 rows x 4 columns per warp step: the shared-memory reads are conflict free and every column's 8 values
-    // are two full 32-byte sectors of its W row
-    const int kk = (lane & 3) | ((lane >> 4) << 2), cc = 4 * warp + ((lane >> 2) & 3);
-    double *Wr = L.W64 + (size_t)s * ld * rld + (size_t)(c0 + cc) * rld;
-    for (int k = kk; k < rld; k += 8) Wr[k] = (k < r) ? Y[k * kW3YS + cc] : 0.0;
+    // measurement-row major panel: row k of the tile is 256 contiguous bytes of W64 row k (lane = column: conflict-free reads,
+    // full-line writes)
+    double *Wg = L.W64 + (size_t)s * ld * rld + c0 + lane;
+    for (int k = warp; k < rld; k += 8) Wg[(size_t)k * ld] = (k < r) ? Y[k * kW3YS + lane] : 0.0;
   }
   REKF_WSTAMP2();
   if (L.Wq) {
