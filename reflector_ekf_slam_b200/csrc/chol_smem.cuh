@@ -21,7 +21,13 @@
 //     against its column tiles, A fragments in registers;
 //   * L goes back to global memory once, at the end.
 // 256 threads (the per-thread 32-double rows stay in registers), one CTA per session.
-// Larger r (config C4) falls back to k_cholesky (global-memory panels).
+//
+// Larger r (config C4: r = 400, a 641 KB triangle) is factored in two levels with the same kernel (chol_split):
+//   S = [S11 S21ᵀ; S21 S22],  r1 = 32·⌊r/64⌋ rows in the leading block, both halves <= kCholResidentMax:
+//   (1) this kernel on S11 (part 1) — the row that follows (row r1 of S21) rides along in the ν position and comes out solved;
+//   (2) k_chol_trsm_rows: the other rows of S21 and ν against L11 (DMMA TRSM, the same tile routine as k_solve_w3);
+//   (3) k_chol_syrk: S22 −= L21·L21ᵀ (incl. the ν row);  (4) this kernel on the updated S22 with ν (part 2).
+// Frames with r beyond 2·kCholResidentMax − 16 (only GPS rows on top of 200 reflectors) fall back to k_cholesky.
 #pragma once
 #include "rekf_device.cuh"
 #include "rekf_kernels.cuh"
@@ -29,6 +35,14 @@
 namespace rekf {
 
 constexpr int kCholSmemThreads = 256;
+constexpr int kCholResidentMax = 208;   // rows one CTA's shared memory holds (219 KB of packed panels)
+
+// two-level split of a frame with r measurement rows: 0 = single pass, else r1 (a multiple of 32), -1 = too large for two levels
+__host__ __device__ inline int chol_split(int r) {
+  if (r <= kCholResidentMax) return 0;
+  const int r1 = 32 * (r / 64);
+  return (r1 <= kCholResidentMax && r - r1 <= kCholResidentMax) ? r1 : -1;
+}
 
 // Packed COLUMN-major block columns — the same orientation as the global S / L buffer, so that the triangle moves in
 // and out as one bulk copy (cp.async.bulk) per column.  Block column b holds columns 32b..32b+31, rows 32b..R1-1
@@ -55,6 +69,19 @@ inline size_t smem_chol_resident(int rcap) {
 __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b, double c0, double c1) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
                : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
+}
+
+// 1/sqrt(d) for a pivot of an SPD matrix, branch-free: the hardware's 23-bit seed (MUFU.RSQ64H) and two Newton steps (46, then
+// > 53 bits).  libdevice's rsqrt() carries special-case branches; inside the fully unrolled pivot loop they end the basic
+// block, and the scheduler could no longer start the next pivot's chain under the current column's rank-1 update — the
+// diagonal blocks ran at ~240 cycles per column instead of the ~130 of the dependent chain.
+__device__ __forceinline__ double pivot_rsqrt(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double h = 0.5 * d;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  return y;
 }
 
 // trailing update A[i][c] −= Σ_k P[i][k]·P[c][k] on the fp64 tensor pipe for the 8-column tiles ct_lo..ct_hi (counted
@@ -106,18 +133,24 @@ __device__ __forceinline__ void chol_trailing(double *A, const int *tab, const d
   }
 }
 
-__global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L) {
+// part 0: the whole matrix (frames with r <= kCholResidentMax; larger frames: nothing).  part 1 / 2: the leading / trailing
+// block of a split frame (nothing for frames that are not split).
+__global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L, int part) {
   timeline_mark(L, 3);
   extern __shared__ __align__(128) double sm_d[];
   const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
-  const int r = st.r;
-  if (r == 0) return;
+  const int r_frame = st.r;
+  if (r_frame == 0) return;
+  const int split = chol_split(r_frame);
+  if (split < 0 || (split == 0) != (part == 0)) return;
+  const int row0 = part == 2 ? split : 0;                    // first row / column of this pass's block
+  const int r = part == 1 ? split : r_frame - row0;          // its size; row r of the block rides along as "ν"
   const int R1 = r + 1;
   const int nblk = (r + kCholNb - 1) / kCholNb;
   const int sld = L.sld;
-  double *Sb = L.Sbuf + (size_t)s * L.rld * sld;
-  double *Dinv = L.Dinv + (size_t)s * (L.rld / kCholNb) * kCholNb * kCholNb;
+  double *Sb = L.Sbuf + (size_t)s * L.rld * sld + (size_t)row0 * sld + row0;
+  double *Dinv = L.Dinv + ((size_t)s * (L.rld / kCholNb) + row0 / kCholNb) * kCholNb * kCholNb;
   double *A = sm_d;                                         // packed block columns
   double *cb = sm_d + chol_col_off(R1, nblk);               // [2][32] column broadcast buffer of the panel warp
   double *invd = cb + 64;                                   // [2][32] reciprocals of the diagonal, ping-pong by block parity
@@ -191,15 +224,22 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L)
       double d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int j = 0; j < kCholNb; ++j) {
-        if (!(d > 0.0)) bad = true;
-        const double inv = rsqrt(d);
+        bad |= !(d > 0.0);
+        const double inv = pivot_rsqrt(d);
         const double l = (lane == j) ? d * inv : a[j] * inv;
         if (lane == j) rinv[j] = inv;
         if (j + 1 < kCholNb) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);   // next pivot, early
         cb[(j & 1) * 32 + lane] = l;
         __syncwarp();
+        {
+          const double2 *cb2 = reinterpret_cast<const double2 *>(cb + (j & 1) * 32);   // 16-byte broadcast reads
 #pragma unroll
-        for (int jj = j + 1; jj < kCholNb; ++jj) a[jj] = fma(-l, cb[(j & 1) * 32 + jj], a[jj]);
+          for (int p = (j + 1) >> 1; p < kCholNb / 2; ++p) {
+            const double2 v = cb2[p];
+            if (2 * p > j) a[2 * p] = fma(-l, v.x, a[2 * p]);
+            a[2 * p + 1] = fma(-l, v.y, a[2 * p + 1]);
+          }
+        }
         a[j] = l;
       }
 #pragma unroll
@@ -268,6 +308,46 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L)
   if (lane == 0) tlog[64 + warp] = (double)clock64();       // per-warp finish stamps
 #endif
   if (bad && lane == 0) atomicOr(&st.flags, FLAG_NOT_SPD);
+}
+
+// ---- split frames, stage 3: S22 −= L21·L21ᵀ for rows / columns r1..r (row r = ν; its column does not exist), lower triangle.
+//      L21[i][k] = Sb[k][i] (column-major): a 32-row slice of a column is one contiguous 256-byte read.  grid (tiles, 1, Sg) ----
+__global__ void __launch_bounds__(256) k_chol_syrk(Layout L) {
+  const int s = L.s0 + blockIdx.z;
+  const int r = L.st[s].r;
+  const int r1 = chol_split(r);
+  if (r1 <= 0) return;
+  const int nt = (r + 1 - r1 + 31) / 32;                     // 32-row tiles of the trailing block incl. ν
+  int t = blockIdx.x, ti = 0;
+  while (t > ti) { t -= ti + 1; ++ti; }                      // tile (ti, tj), tj <= ti
+  const int tj = t;
+  if (ti >= nt) return;
+  const int sld = L.sld;
+  double *Sb = L.Sbuf + (size_t)s * L.rld * sld;
+  __shared__ double As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;    // thread: column tj*32 + tx of rows ti*32 + ty + 8u
+  const int i0 = r1 + 32 * ti, j0 = r1 + 32 * tj;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < r1; k0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+      const int kk = e >> 5, ii = e & 31;
+      As[kk][ii] = (i0 + ii <= r) ? Sb[(size_t)(k0 + kk) * sld + i0 + ii] : 0.0;
+      Bs[kk][ii] = (j0 + ii <= r) ? Sb[(size_t)(k0 + kk) * sld + j0 + ii] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const double b = Bs[kk][tx];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fma(As[kk][ty + 8 * u], b, acc[u]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + ty + 8 * u, j = j0 + tx;
+    if (i <= r && j < r && j <= i) Sb[(size_t)j * sld + i] -= acc[u];
+  }
 }
 
 }  // namespace rekf

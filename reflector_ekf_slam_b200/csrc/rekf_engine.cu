@@ -267,25 +267,42 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     ProfScope p(h, K_FRONT, stream);
     k_observation_front<<<L.Sg, 1024, smem_front(L), stream>>>(L, in);
   }
+  {
+    ProfScope p(h, K_INNOV, stream);
+    const int g = (L.rcap + 15) / 16;
+    k_innovation<<<dim3(g, g, L.Sg), dim3(16, 16), 0, stream>>>(L);
+  }
+  if (h->solve_w2) CK(cudaEventRecord(grp.ev_fork, stream));
+  {
+    ProfScope p(h, K_CHOL, stream);
+    if (h->chol_resident) {
+      const size_t sm = smem_chol_resident(std::min(L.rcap, kCholResidentMax));
+      k_cholesky_smem<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 0);
+      if (L.rcap > kCholResidentMax) {
+        // two-level factorisation of frames with more rows than one SM holds (chol_smem.cuh); every stage decides on the
+        // device whether the frame is split, so the chain is static
+        k_cholesky_smem<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 1);
+        k_chol_trsm_rows<<<dim3((L.rcap - 32 + kW3Cols - 1) / kW3Cols, 1, L.Sg), 256, smem_solve_w3(L.rld), stream>>>(L);
+        const int nt = (L.rcap + 1 + 31) / 32;
+        k_chol_syrk<<<dim3(nt * (nt + 1) / 2, 1, L.Sg), 256, 0, stream>>>(L);
+        k_cholesky_smem<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 2);
+        k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L, 1);      // frames too large even for two levels
+        h->launches += 5;
+      }
+    } else {
+      k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L, 0);
+    }
+  }
   if (h->solve_w2) {
-    // fork: Y = H·Σ needs only the match lists and the predicted Σ — a parallel branch (under capture: of the step graph)
-    CK(cudaEventRecord(grp.ev_fork, stream));
+    // fork: Y = H·Σ needs only the match lists and the predicted Σ — a parallel branch (under capture: of the step graph) that
+    // runs in the shadow of the Cholesky (one CTA per session, the rest of the GPU idle).  It is forked behind k_innovation
+    // and issued after the Cholesky launch: beside k_innovation its ~1000 short blocks tripled that kernel's latency.
     CK(cudaStreamWaitEvent(grp.side_stream, grp.ev_fork, 0));
     {
       ProfScope p(h, K_GATHER, grp.side_stream);
       k_gather_y<<<dim3(L.ld / 128, (L.rcap / 2 + kGYPairs - 1) / kGYPairs, L.Sg), 256, 0, grp.side_stream>>>(L);
     }
     CK(cudaEventRecord(grp.ev_join, grp.side_stream));
-  }
-  {
-    ProfScope p(h, K_INNOV, stream);
-    const int g = (L.rcap + 15) / 16;
-    k_innovation<<<dim3(g, g, L.Sg), dim3(16, 16), 0, stream>>>(L);
-  }
-  {
-    ProfScope p(h, K_CHOL, stream);
-    if (h->chol_resident) k_cholesky_smem<<<L.Sg, kCholSmemThreads, smem_chol_resident(L.rcap), stream>>>(L);
-    else k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L);
   }
   if (h->solve_w2) CK(cudaStreamWaitEvent(stream, grp.ev_join, 0));   // join before the TRSM
   CK(cudaGetLastError());
@@ -433,7 +450,12 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
   for (int i = 0; i < Group::kSlots; ++i) CK(cudaEventCreateWithFlags(&g.slot_done[i], cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.phase_ev, cudaEventDisableTiming));
-  CK(cudaStreamCreateWithFlags(&g.side_stream, cudaStreamNonBlocking));
+  {
+    // the side branch (Y = H·Σ: ~1000 short blocks) must not crowd the latency-bound main chain out of the SMs: lowest priority
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&g.side_stream, cudaStreamNonBlocking, least));
+  }
   CK(cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&g.ev_join, cudaEventDisableTiming));
   CK(cudaMallocHost(&g.pose_host, sizeof(double) * 3 * S * Group::kPoseSlots));
@@ -537,7 +559,9 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   if (opts->stream) {
     h->stream = static_cast<cudaStream_t>(opts->stream);
   } else {
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    int least = 0, greatest = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CK(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
     h->own_stream = true;
   }
   Layout &L = h->L;
@@ -620,7 +644,9 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
     for (int g = 0; g < G; ++g) {
       const int lo = (int)((long long)sessions * g / G), hi = (int)((long long)sessions * (g + 1) / G);
       cudaStream_t st = nullptr;
-      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      int least = 0, greatest = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      CK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, greatest));
       if ((rc = init_group(h, h->groups[g], lo, hi - lo, g + 1, st, true))) return rc;
     }
   }
@@ -635,11 +661,12 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   CK(cudaFuncSetAttribute(k_cholesky, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol(L)));
   h->solve_w2 = smem_solve_w3(L.rld) <= 227 * 1024;
   if (h->solve_w2) CK(cudaFuncSetAttribute(k_solve_w3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w3(L.rld)));
-  h->chol_resident = smem_chol_resident(L.rcap) <= 227 * 1024;
-  // the resident Cholesky does not emit the diagonal-block inverses the old TRSM kernel needs: use them as a pair
-  h->chol_resident = h->solve_w2 = (h->chol_resident && h->solve_w2);
-  if (h->chol_resident)
-    CK(cudaFuncSetAttribute(k_cholesky_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(L.rcap)));
+  // the resident Cholesky (one or two levels) and the DMMA TRSM come as a pair: both need the operands of a frame in one SM
+  h->chol_resident = h->solve_w2;
+  if (h->chol_resident) {
+    CK(cudaFuncSetAttribute(k_cholesky_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(std::min(L.rcap, kCholResidentMax))));
+    CK(cudaFuncSetAttribute(k_chol_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w3(L.rld)));
+  }
   CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
   if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
     const char *why = syrk_tc_init(h->tc, L);

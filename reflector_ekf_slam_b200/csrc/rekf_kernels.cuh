@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(256) k_innovation(Layout L) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kGYPairs = 16;
 __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
-  timeline_mark(L, 3);
+  timeline_mark(L, 8);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
@@ -564,12 +564,14 @@ __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kPS = kCholNb + 1;   // padded panel pitch in shared memory
 
-__global__ void __launch_bounds__(1024, 1) k_cholesky(Layout L) {
+// only_oversize: take only the frames the two-level resident path (chol_smem.cuh) cannot (r beyond 2·208 − 16 rows)
+__global__ void __launch_bounds__(1024, 1) k_cholesky(Layout L, int only_oversize) {
   extern __shared__ double sm_d[];
   const int s = L.s0 + blockIdx.x;
   SessionState &st = L.st[s];
   const int r = st.r;
   if (r == 0) return;
+  if (only_oversize && (r <= 208 || (32 * (r / 64) <= 208 && r - 32 * (r / 64) <= 208))) return;
   const int sld = L.sld;
   double *Sb = L.Sbuf + (size_t)s * L.rld * sld;
   double *P = sm_d;                                  // [(rcap+1)][kPS] current block column (rows J..r)

@@ -31,66 +31,16 @@ inline size_t smem_solve_w3(int rld) {
 // DMMA A-fragment loads (8 rows x 4 k)
 __device__ __forceinline__ int swz(int row) { return ((row & 3) << 2) | ((row >> 2) & 3); }
 
-__global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
-  timeline_mark(L, 4);
-  extern __shared__ double sm_d[];
-  const int s = L.s0 + blockIdx.z;
-  const SessionState &st = L.st[s];
-  const int r = st.r;
-  if (r == 0) return;
-  const int n = internal_dim(st.N);
-  const int c0 = blockIdx.x * kW3Cols;
-  if (c0 >= round_up(n, kSigmaTile)) return;
-  const int ld = L.ld, sld = L.sld, rld = L.rld;
-  const double *Sg = L.sigma + (size_t)s * ld * ld;
-  const double *Sb = L.Sbuf + (size_t)s * rld * sld;
-  double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
-  double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [2][64][32] swizzled chunks of an L panel (double buffer)
-  double *Xs = Lp + 2 * 32 * kW3LP;                   // [32][32] swizzled inverse of the current diagonal block
-  double *nu = Xs + 32 * 32;                          // [rld] L⁻¹ν (row r of the factor), staged once
-  int *sexp = reinterpret_cast<int *>(nu + rld);      // [32]
-  double *sdiag = reinterpret_cast<double *>(sexp + 64);   // [32] prior Σ[c][c] of this CTA's columns, fetched up front
-  if (threadIdx.x < kW3Cols) sdiag[threadIdx.x] = Sg[(size_t)min(c0 + (int)threadIdx.x, ld - 1) * (ld + 1)];
-  for (int k = threadIdx.x; k < r; k += 256) nu[k] = Sb[(size_t)k * sld + r];   // visible after the gather's barriers
+// Blocked forward substitution L·W = Y on the fp64 tensor pipe, in place in the shared-memory tile Y ([rows][kW3YS], 32 columns).
+// L (column-major lower triangle, pitch sld) and the inverses of its 32x32 diagonal blocks (Dinv) are read from global / L2:
+// L chunks and block inverses arrive by cp.async one stage ahead of their use (double-buffered chunks), so the L2 latency of
+// the operand stream is hidden behind the DMMAs of the previous stage.  All 256 threads of the CTA call it; Y must be complete
+// (or in flight in an earlier cp.async group); on return every thread may read W from Y.
+__device__ __forceinline__ void trsm_forward_tile(double *Y, double *Lp, double *Xs, const double *Sb, const double *Dinv, int r,
+                                                  int sld, int rld) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;             // DMMA fragment coordinates
   const int nt = warp & 3, rp = warp >> 2;            // this warp's 8-column tile and row-tile parity
-  const int r32 = round_up(r, 32);
-#ifdef REKF_SOLVE_TIMING
-  double *tlog = L.innov + (size_t)s * L.rcap;        // cycle stamps of CTA 0 (thread 0)
-  int tl = 0;
-#define REKF_WSTAMP() do { if (tid == 0 && blockIdx.x == 0) tlog[tl++] = (double)clock64(); } while (0)
-#else
-#define REKF_WSTAMP() do { } while (0)
-#endif
-#ifdef REKF_SOLVE_TIMING2
-#define REKF_WSTAMP2() REKF_WSTAMP()
-#else
-#define REKF_WSTAMP2() do { } while (0)
-#endif
-  REKF_WSTAMP();
-
-  // ---- Y tile: rows 0..r-1 of Y = H·Σ (k_gather_y wrote them beside the Cholesky), this CTA's 32 columns = 256 contiguous
-  //      bytes per row, 16-byte cp.async; rows r..r32-1 of the tile are zero --------------------------------------------
-  {
-    const double *Yg = L.Ybuf + (size_t)s * rld * ld + c0;
-    for (int e = tid; e < r32 * 16; e += 256) {
-      const int q = e >> 4, cc = (e & 15) * 2;
-      double *dst = Y + q * kW3YS + cc;
-      if (q < r) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(Yg + (size_t)q * ld + cc) : "memory");
-      } else {
-        dst[0] = 0.0; dst[1] = 0.0;
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");   // waited for together with the first L / X stage below
-  }
-  REKF_WSTAMP();
-
-  // ---- blocked forward substitution L·W = Y on the fp64 tensor pipe ---------------------------------------
-  // L chunks and block inverses arrive by cp.async one stage ahead of their use (double-buffered chunks), so
-  // the L2 latency of the operand stream is hidden behind the DMMAs of the previous stage.
-  const double *Dinv = L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb;
   auto cp8 = [](double *dst, const double *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
   };
@@ -124,7 +74,6 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
     const int jb = min(kCholNb, r - J);
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                  // X_J landed; also orders the gather / previous trailing update
-    REKF_WSTAMP();
     // W_J = X_J·Y_J : 4 row tiles x 4 column tiles of 8x8; this warp: column tile nt, row tiles rp and rp+2
     double w0[2], w1[2], u0[2], u1[2];
     w0[0] = w0[1] = w1[0] = w1[1] = u0[0] = u0[1] = u1[0] = u1[1] = 0.0;
@@ -152,7 +101,6 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
       *reinterpret_cast<double2 *>(Y + (J + 8 * rt + g) * kW3YS + 8 * nt + 2 * t4) = make_double2(w0[h], w1[h]);
     }
     __syncthreads();
-    REKF_WSTAMP();
     if (J + jb >= r) break;
     double wb[8];                                     // B fragments of W_J for this warp's column tile
 #pragma unroll
@@ -204,6 +152,92 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+}
+
+// Split frames (chol_smem.cuh), stage 2: rows r1+1..r of S21 (and ν) against L11 — L21[i][:] = S21[i][:]·L11⁻ᵀ.  Row i of S21 is a
+// right-hand side of L11·x = S21[i][:]ᵀ, so 32 rows form one tile of trsm_forward_tile; S21[i][k] = Sb[k][i] is contiguous in i.
+// grid (ceil((rcap - 32) / 32), 1, Sg).
+__global__ void __launch_bounds__(256, 1) k_chol_trsm_rows(Layout L) {
+  extern __shared__ double sm_d[];
+  const int s = L.s0 + blockIdx.z;
+  const int r = L.st[s].r;
+  const int r1 = chol_split(r);
+  if (r1 <= 0) return;
+  const int c0 = r1 + 1 + blockIdx.x * kW3Cols;       // first absolute row of this tile (row r1 itself rode along in pass 1)
+  if (c0 > r) return;
+  const int sld = L.sld, rld = L.rld;
+  double *Sb = L.Sbuf + (size_t)s * rld * sld;
+  double *Y = sm_d;                                   // [r1 + 8][kW3YS]
+  double *Lp = Y + (size_t)(rld + 8) * kW3YS;
+  double *Xs = Lp + 2 * 32 * kW3LP;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < r1 * 32; e += 256) {
+    const int k = e >> 5, cc = e & 31;
+    Y[k * kW3YS + cc] = (c0 + cc <= r) ? Sb[(size_t)k * sld + c0 + cc] : 0.0;
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  trsm_forward_tile(Y, Lp, Xs, Sb, L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb, r1, sld, rld);
+  for (int e = tid; e < r1 * 32; e += 256) {
+    const int k = e >> 5, cc = e & 31;
+    if (c0 + cc <= r) Sb[(size_t)k * sld + c0 + cc] = Y[k * kW3YS + cc];
+  }
+}
+
+__global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
+  timeline_mark(L, 4);
+  extern __shared__ double sm_d[];
+  const int s = L.s0 + blockIdx.z;
+  const SessionState &st = L.st[s];
+  const int r = st.r;
+  if (r == 0) return;
+  const int n = internal_dim(st.N);
+  const int c0 = blockIdx.x * kW3Cols;
+  if (c0 >= round_up(n, kSigmaTile)) return;
+  const int ld = L.ld, sld = L.sld, rld = L.rld;
+  const double *Sg = L.sigma + (size_t)s * ld * ld;
+  const double *Sb = L.Sbuf + (size_t)s * rld * sld;
+  double *Y = sm_d;                                   // [rld + 8][kW3YS] (the last row tile may overhang r by 7 rows)
+  double *Lp = Y + (size_t)(rld + 8) * kW3YS;         // [2][64][32] swizzled chunks of an L panel (double buffer)
+  double *Xs = Lp + 2 * 32 * kW3LP;                   // [32][32] swizzled inverse of the current diagonal block
+  double *nu = Xs + 32 * 32;                          // [rld] L⁻¹ν (row r of the factor), staged once
+  int *sexp = reinterpret_cast<int *>(nu + rld);      // [32]
+  double *sdiag = reinterpret_cast<double *>(sexp + 64);   // [32] prior Σ[c][c] of this CTA's columns, fetched up front
+  if (threadIdx.x < kW3Cols) sdiag[threadIdx.x] = Sg[(size_t)min(c0 + (int)threadIdx.x, ld - 1) * (ld + 1)];
+  for (int k = threadIdx.x; k < r; k += 256) nu[k] = Sb[(size_t)k * sld + r];   // visible after the gather's barriers
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r32 = round_up(r, 32);
+#ifdef REKF_SOLVE_TIMING
+  double *tlog = L.innov + (size_t)s * L.rcap;        // cycle stamps of CTA 0 (thread 0)
+  int tl = 0;
+#define REKF_WSTAMP() do { if (tid == 0 && blockIdx.x == 0) tlog[tl++] = (double)clock64(); } while (0)
+#else
+#define REKF_WSTAMP() do { } while (0)
+#endif
+#ifdef REKF_SOLVE_TIMING2
+#define REKF_WSTAMP2() REKF_WSTAMP()
+#else
+#define REKF_WSTAMP2() do { } while (0)
+#endif
+  REKF_WSTAMP();
+
+  // ---- Y tile: rows 0..r-1 of Y = H·Σ (k_gather_y wrote them beside the Cholesky), this CTA's 32 columns = 256 contiguous
+  //      bytes per row, 16-byte cp.async; rows r..r32-1 of the tile are zero --------------------------------------------
+  {
+    const double *Yg = L.Ybuf + (size_t)s * rld * ld + c0;
+    for (int e = tid; e < r32 * 16; e += 256) {
+      const int q = e >> 4, cc = (e & 15) * 2;
+      double *dst = Y + q * kW3YS + cc;
+      if (q < r) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(Yg + (size_t)q * ld + cc) : "memory");
+      } else {
+        dst[0] = 0.0; dst[1] = 0.0;
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // waited for together with the first L / X stage below
+  }
+  REKF_WSTAMP();
+
+  trsm_forward_tile(Y, Lp, Xs, Sb, L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb, r, sld, rld);
   REKF_WSTAMP();
 
   // ---- μ += Wᵀ·(L⁻¹ν) (:306), θ wrapped (:307); exact diagonal of the downdate -------------------------------

@@ -30,10 +30,10 @@ e = raw[1:1 + n]
 t = (e >> np.uint64(12)).astype(np.float64) / 1e3
 kid = ((e >> np.uint64(8)) & np.uint64(15)).astype(int)
 s0 = (e & np.uint64(255)).astype(int)
-names = ["odo", "front", "innov", "chol", "solve", "syrkf64", "syrk", "augment"]
+names = ["odo", "front", "innov", "chol", "solve", "syrkf64", "syrk", "augment", "gather_y"] + ["?"] * 7
 order = np.argsort(t)
 t, kid, s0 = t[order], kid[order], s0[order]
-per_step = 8 * G
+per_step = 8 * G   # kernels per step: front, gather_y, innov, chol, solve, syrkf64, syrk, augment
 sel = slice(len(t) - 3 * per_step, len(t))
 t0 = t[sel][0]
 prev = {}
