@@ -257,3 +257,47 @@ def test_predict_state_is_non_mutating():
     mu_n, sig_n = n.predict_state(n.time + 0.25)
     assert np.array_equal(before, o.GetStateVector())
     assert np.abs(mu - mu_n).max() < 1e-13 and rel_fro(sig, sig_n) < 1e-13
+
+
+def test_oracle_under_asan_and_ubsan(tmp_path):
+    """Host sanitizers on the C restatement: `make -C oracle asan` (-fsanitize=address,undefined), a T0 and a T1
+    stream in both algebra modes plus the map text round trip, in a child process with the sanitizer runtime preloaded."""
+    import shutil
+    import subprocess
+    import sys
+    if not os.path.exists("/usr/bin/gcc"):
+        pytest.skip("/usr/bin/gcc not available")
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    asan = subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not found")
+    subprocess.run(["make", "-s", "-C", os.path.join(here, "oracle"), "asan"], check=True)
+    lib = os.path.join(here, "oracle", "_build", "liboracle_asan.so")
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not found")
+    code = f"""
+import sys, ctypes
+sys.path.insert(0, {here!r})
+from oracle import pyoracle
+from oracle.pyoracle import AS_WRITTEN, STRUCTURED, Oracle
+from reflector_ekf_slam_b200.synth import make_stream
+lib = ctypes.CDLL({lib!r})
+pyoracle._bind(lib, ref=False)
+for cfg, steps in (("T0", 12), ("T1", 6)):
+    st = make_stream(cfg, steps)
+    for alg in (AS_WRITTEN, STRUCTURED):
+        o = Oracle(algebra=alg, lib=lib, odom_model=st["model"])
+        for k in range(len(st["odom"])):
+            o.HandleOdometryMessage(*st["odom"][k])
+            o.HandleObservationMessage(st["obs_time"][k], st["obs_xy"][k, : st["obs_count"][k]])
+        o.PredictState(o.GetLatestTime() + 0.01)
+        assert o.save_map_txt({str(tmp_path / "m")!r}) == 0
+        o.load_map_txt({str(tmp_path / "m.txt")!r})
+        o.close()
+print("asan run complete")
+"""
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0", UBSAN_OPTIONS="print_stacktrace=1")
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert "asan run complete" in res.stdout
+    assert "AddressSanitizer" not in res.stderr and "runtime error" not in res.stderr, res.stderr[-3000:]

@@ -276,5 +276,14 @@ def test_replay_entry_point_bag_to_map_file(engine_lib, tmp_path):
     xy = np.array([float(v) for v in lines[0].split(",") if v]).reshape(-1, 2)
     cov = np.array([float(v) for v in lines[1].split(",") if v]).reshape(-1, 4)
     assert len(xy) == len(cov) == len(REFLECTORS)
-    for r in REFLECTORS:
-        assert np.linalg.norm(xy - np.array(r), axis=1).min() < 0.08
+    # the filter's frame is the robot's base_link at the FIRST scan (init pose 0 at that stamp, ros_node.cc:424-441)
+    x0 = y0 = th0 = 0.0
+    for _ in range(5):
+        thm = th0 + 0.5 * 0.3 * 0.02
+        x0 += 0.4 * math.cos(thm) * 0.02
+        y0 += 0.4 * math.sin(thm) * 0.02
+        th0 += 0.3 * 0.02
+    c, s_ = math.cos(-th0), math.sin(-th0)
+    for (rx, ry) in REFLECTORS:
+        ex, ey = c * (rx - x0) - s_ * (ry - y0), s_ * (rx - x0) + c * (ry - y0)
+        assert np.linalg.norm(xy - np.array([ex, ey]), axis=1).min() < 0.08, (ex, ey, xy)
