@@ -269,7 +269,10 @@ def test_replay_entry_point_bag_to_map_file(engine_lib, tmp_path):
     is exact in this world, so the map lands within centimetres) and writes the reference's two-line map file."""
     from reflector_ekf_slam_b200.replay.__main__ import main
     path = str(tmp_path / "world.bag")
-    write_bag(path, drive(sim_steps=25, scan_time=0.1))
+    # gentle rotation and a short scan: the reference's extrapolator turns beams the WRONG way when it extrapolates backwards
+    # (pose_extrapolator.cc:115-127, restated as is), so under rotation its "corrected" centres are biased by ~w·scan_time·range
+    tw = (0.4, 0.0, 0.1)
+    write_bag(path, drive(sim_steps=25, scan_time=0.05, twist=tw))
     out = str(tmp_path / "map")
     assert main([path, "--out", out, "--max-landmarks", "16"]) == 0
     lines = open(out + ".txt").read().split("\n")
@@ -279,10 +282,10 @@ def test_replay_entry_point_bag_to_map_file(engine_lib, tmp_path):
     # the filter's frame is the robot's base_link at the FIRST scan (init pose 0 at that stamp, ros_node.cc:424-441)
     x0 = y0 = th0 = 0.0
     for _ in range(5):
-        thm = th0 + 0.5 * 0.3 * 0.02
-        x0 += 0.4 * math.cos(thm) * 0.02
-        y0 += 0.4 * math.sin(thm) * 0.02
-        th0 += 0.3 * 0.02
+        thm = th0 + 0.5 * tw[2] * 0.02
+        x0 += tw[0] * math.cos(thm) * 0.02
+        y0 += tw[0] * math.sin(thm) * 0.02
+        th0 += tw[2] * 0.02
     c, s_ = math.cos(-th0), math.sin(-th0)
     for (rx, ry) in REFLECTORS:
         ex, ey = c * (rx - x0) - s_ * (ry - y0), s_ * (rx - x0) + c * (ry - y0)
