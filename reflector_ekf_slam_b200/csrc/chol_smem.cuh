@@ -281,8 +281,15 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
         for (int jj = 0; jj < kCholNb; ++jj) Dg[jj * kCholNb + c] = a[jj];
       }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's panel writes → visible to the bulk engine
     __syncthreads();
     REKF_TSTAMP();
+    // block column b of L is final: it goes back to global memory now, in the shadow of the remaining blocks (the last block
+    // column waits for the ν fix-up after the loop)
+    if (cb_b == b && b < nblk - 1 && col_bytes) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
 
     // ---- phase 3: the panel's update of block column b+1 only (what the next diagonal block and its rows need);
     //      the rest of the trailing matrix is updated in the shadow of the next factorisation (phase 1) ------------
@@ -295,13 +302,15 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
     col[jb_last] = col[kCholNb];
   }
 
-  // ---- publish L (k_solve_w3 reads it from global / L2): the same per-column bulk copies, the other way ---------------
+  // ---- publish the last block column of L (the others left inside the loop): the same per-column bulk copies, the other way ----
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the panels → visible to the bulk engine
   __syncthreads();
   if (col_bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (cb_b == nblk - 1) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's column (issued above or inside the loop) has landed
   }
   REKF_TSTAMP();
 #ifdef REKF_CHOL_TIMING
