@@ -14,8 +14,11 @@
 //     In its shadow warp 1 inverts the PREVIOUS diagonal block (X = L_bb⁻¹, lane = column of X held in registers,
 //     broadcast reads of L, no shuffles) — the TRSM kernel consumes these inverses — and warps 2-7 apply the previous
 //     panel's rank-32 update to everything right of the current block column;
-//   * phase 2: every row below the block (and the ν row) is owned by one thread, held in registers, and
-//     solved against the diagonal block by column-oriented substitution (31−j independent FMAs per step);
+//   * phase 2: the rows below the block (and the ν row) times the block inverse on the fp64 tensor pipe, P ← P·Xᵀ in 8-row
+//     DMMA tiles (one thread per row solving by substitution was issue-bound: 3-9 k cycles per block against ~1.5 k).
+//     X = L_bb⁻¹ — the inverse the TRSM kernel consumes anyway — costs no extra pass: the panel warp carries the
+//     substitution of the identity along with the factorisation (lane = column of X; step j needs exactly the column of L
+//     that the rank-1 update has just broadcast, one more FMA per value read), in the issue slots the rsqrt chain leaves idle;
 //   * phase 3: the panel's update of the NEXT block column only (all warps) — the one thing the next factorisation
 //     waits for.  Updates run on the fp64 tensor pipe (mma.sync m8n8k4 → DMMA): a warp task is one 8-row tile
 //     against its column tiles, A fragments in registers;
@@ -35,6 +38,7 @@
 namespace rekf {
 
 constexpr int kCholSmemThreads = 256;
+constexpr int kCholXP = 36;              // pitch of the block inverse in shared memory: DMMA A-fragment loads (8 rows x 4 k) 2-way at worst
 constexpr int kCholResidentMax = 208;   // rows one CTA's shared memory holds (219 KB of packed panels)
 
 // two-level split of a frame with r measurement rows: 0 = single pass, else r1 (a multiple of 32), -1 = too large for two levels
@@ -61,7 +65,7 @@ __host__ __device__ inline int chol_col_off(int R1, int b) {
 }
 inline size_t smem_chol_resident(int rcap) {
   const int R1 = rcap + 1, nb = (rcap + kCholNb - 1) / kCholNb;
-  return sizeof(double) * ((size_t)chol_col_off(R1, nb) + 2 * 32 + 2 * 32 + 2 + 8);
+  return sizeof(double) * ((size_t)chol_col_off(R1, nb) + 2 * 32 + 2 * 32 + 2 + 8 + 32 * kCholXP);
 }
 
 // D(8x8) = A(8x4)·B(4x8) + C on the fp64 tensor pipe.  Fragments (lane = 4·g + t): a = A[g][t], b = B[t][g],
@@ -156,6 +160,7 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
   double *invd = cb + 64;                                   // [2][32] reciprocals of the diagonal, ping-pong by block parity
   uint64_t *bar = reinterpret_cast<uint64_t *>(invd + 64);  // transaction barrier of the bulk load
   int *tab = reinterpret_cast<int *>(bar + 2);              // [8] block-column offsets, [8] pitches
+  double *Xs = reinterpret_cast<double *>(tab + 16);        // [32][kCholXP] inverse of the current diagonal block, X[j][k]
   if (threadIdx.x < 8) { tab[threadIdx.x] = chol_col_off(R1, threadIdx.x); tab[8 + threadIdx.x] = chol_lda(R1, threadIdx.x); }
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = NT / 32;
   bool bad = false;
@@ -218,9 +223,9 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
     // ---- phase 1: warp 0 factors the diagonal block; meanwhile warp 1 inverts the previous diagonal block (for the
     //      TRSM kernel) and warps 2.. finish the previous panel's trailing update right of block column b ------------
     if (warp == 0) {
-      double a[kCholNb];
+      double a[kCholNb], x[kCholNb];                        // row `lane` of the block; column `lane` of X = L_bb⁻¹
 #pragma unroll
-      for (int jj = 0; jj < kCholNb; ++jj) a[jj] = (jj <= lane) ? P[jj * lda + lane] : 0.0;
+      for (int jj = 0; jj < kCholNb; ++jj) { a[jj] = (jj <= lane) ? P[jj * lda + lane] : 0.0; x[jj] = (jj == lane) ? 1.0 : 0.0; }
       double d = __shfl_sync(0xffffffffu, a[0], 0);
 #pragma unroll
       for (int j = 0; j < kCholNb; ++j) {
@@ -230,55 +235,64 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
         if (lane == j) rinv[j] = inv;
         if (j + 1 < kCholNb) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);   // next pivot, early
         cb[(j & 1) * 32 + lane] = l;
+        const double xj = x[j] * inv;                        // X[j][lane]: forward substitution of e_lane, step j
         __syncwarp();
         {
-          const double2 *cb2 = reinterpret_cast<const double2 *>(cb + (j & 1) * 32);   // 16-byte broadcast reads
+          const double2 *cb2 = reinterpret_cast<const double2 *>(cb + (j & 1) * 32);   // column j of L: 16-byte broadcast reads
 #pragma unroll
           for (int p = (j + 1) >> 1; p < kCholNb / 2; ++p) {
             const double2 v = cb2[p];
-            if (2 * p > j) a[2 * p] = fma(-l, v.x, a[2 * p]);
+            if (2 * p > j) { a[2 * p] = fma(-l, v.x, a[2 * p]); x[2 * p] = fma(-xj, v.x, x[2 * p]); }
             a[2 * p + 1] = fma(-l, v.y, a[2 * p + 1]);
+            x[2 * p + 1] = fma(-xj, v.y, x[2 * p + 1]);
           }
         }
         a[j] = l;
+        x[j] = xj;
       }
+      double *Dg = Dinv + (size_t)b * kCholNb * kCholNb;     // X[j][c], row-major: what the TRSM kernel consumes
 #pragma unroll
-      for (int jj = 0; jj < kCholNb; ++jj)
+      for (int jj = 0; jj < kCholNb; ++jj) {
         if (jj <= lane) P[jj * lda + lane] = a[jj];
+        Xs[jj * kCholXP + lane] = x[jj];
+        Dg[jj * kCholNb + lane] = x[jj];
+      }
     } else if (b > 0) {
       chol_trailing(A, tab, A + chol_col_off(R1, b - 1), chol_lda(R1, b - 1), J - kCholNb, R1, r, 4, 1 << 30, warp - 1, NW - 1, lane);
     }
     __syncthreads();
     REKF_TSTAMP();
 
-    // ---- phase 2: rows below the block (incl. ν), one thread per row, substitution in registers; column j of the
-    //      diagonal block is contiguous: 16-byte broadcast reads.  32 more threads run the same substitution on the rows
-    //      of the identity: their results are the columns of X = L_bb⁻¹, the block inverse the TRSM kernel consumes -----
-    for (int ii = kCholNb + tid; ii < rows + kCholNb; ii += NT) {
-      const bool real = ii < rows;
-      const int c = ii - rows;                               // identity row (column of X) when !real
-      double a[kCholNb];
+    // ---- phase 2: rows below the block (incl. ν): P ← P·Xᵀ, i.e. out[i][j] = Σ_{k<=j} P[i][k]·X[j][k], on the fp64 tensor pipe.
+    //      Formed transposed like the trailing update — D[m = column j][n = row i] — so that a lane's accumulator pair is two
+    //      consecutive rows of one column: one 16-byte access in the column-major panel.  A warp task is one 8-row tile: all of
+    //      its 32 old values per row are in registers (B fragments) before the first result is written, so it runs in place ----
+    {
+      const int g = lane >> 2, t4 = lane & 3;
+      const int below = rows - kCholNb;
+      const int nrt2 = (below + 7) >> 3;
+      for (int rt = warp; rt < nrt2; rt += NW) {
+        const int irow = kCholNb + 8 * rt + g;
+        const double *bp = P + t4 * lda + min(irow, rows - 1);
+        double bf[8];
 #pragma unroll
-      for (int jj = 0; jj < kCholNb; ++jj) a[jj] = real ? P[jj * lda + ii] : ((jj == c) ? 1.0 : 0.0);
+        for (int ks = 0; ks < 8; ++ks) bf[ks] = bp[4 * ks * lda];
+        __syncwarp();
+        const int r0 = kCholNb + 8 * rt + 2 * t4;            // this lane's two result rows
 #pragma unroll
-      for (int j = 0; j < kCholNb; ++j) {
-        const double l = a[j] * rinv[j];
-        const double *lc = P + j * lda;                      // column j of the diagonal block
+        for (int jt = 0; jt < 4; ++jt) {
+          const double *xf = Xs + (8 * jt + g) * kCholXP + t4;
+          double c0 = 0.0, c1 = 0.0, e0 = 0.0, e1 = 0.0;
 #pragma unroll
-        for (int p = (j + 1) >> 1; p < kCholNb / 2; ++p) {
-          const double2 v = *reinterpret_cast<const double2 *>(lc + 2 * p);
-          if (2 * p > j) a[2 * p] = fma(-l, v.x, a[2 * p]);
-          a[2 * p + 1] = fma(-l, v.y, a[2 * p + 1]);
+          for (int ks = 0; ks < 2 * (jt + 1); ks += 2) {       // X is lower triangular: k < 8(jt+1)
+            dmma884(c0, c1, xf[4 * ks], bf[ks], c0, c1);
+            dmma884(e0, e1, xf[4 * (ks + 1)], bf[ks + 1], e0, e1);
+          }
+          c0 += e0; c1 += e1;
+          double *op = P + (8 * jt + g) * lda + r0;
+          if (r0 + 1 < rows) *reinterpret_cast<double2 *>(op) = make_double2(c0, c1);
+          else if (r0 < rows) op[0] = c0;
         }
-        a[j] = l;
-      }
-      if (real) {
-#pragma unroll
-        for (int jj = 0; jj < kCholNb; ++jj) P[jj * lda + ii] = a[jj];
-      } else {
-        double *Dg = Dinv + (size_t)b * kCholNb * kCholNb;   // X[j][c], row-major
-#pragma unroll
-        for (int jj = 0; jj < kCholNb; ++jj) Dg[jj * kCholNb + c] = a[jj];
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this thread's panel writes → visible to the bulk engine
