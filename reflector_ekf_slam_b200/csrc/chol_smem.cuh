@@ -140,6 +140,7 @@ __device__ __forceinline__ void chol_trailing(double *A, const int *tab, const d
 // part 0: the whole matrix (frames with r <= kCholResidentMax; larger frames: nothing).  part 1 / 2: the leading / trailing
 // block of a split frame (nothing for frames that are not split).
 __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L, int part) {
+  pdl_wait();
   timeline_mark(L, 3);
   extern __shared__ __align__(128) double sm_d[];
   const int s = L.s0 + blockIdx.x;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
 
   const int jb_last = r - (nblk - 1) * kCholNb;             // true width of the last block
   for (int b = 0; b < nblk; ++b) {
+    if (b == nblk - 1) pdl_trigger();                       // the last block: the TRSM kernel may be launched (it waits in pdl_wait())
     const int J = b * kCholNb;
     const int lda = chol_lda(R1, b);
     double *P = A + chol_col_off(R1, b);                    // element (J + i, J + c) at P[c * lda + i]

@@ -132,6 +132,13 @@ __device__ __forceinline__ void timeline_mark(const Layout &L, int kernel_id) {
     if (k + 1 < (unsigned long long)kTimelineCap) L.tlog[k + 1] = (t << 12) | ((unsigned long long)kernel_id << 8) | (unsigned long long)(L.s0 & 255);
   }
 }
+// Programmatic dependent launch (the kernels of a step form a chain in one stream / graph branch): pdl_wait() blocks until the
+// preceding kernel of the chain has completed and flushed; pdl_trigger() lets the NEXT kernel of the chain be launched (its
+// blocks then sit in pdl_wait()), so that its launch latency and prologue overlap this kernel's tail.  Both are no-ops for a
+// kernel launched without the attribute.  Triggers sit a few microseconds before a kernel's end, not at its start: blocks of
+// a dependent that wait for tens of microseconds would hold the SMs the other pipeline group needs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }
 // offset of Σ[i][j] in the upper-triangle-only storage
 __host__ __device__ __forceinline__ size_t sym_idx(int i, int j, int ld) {

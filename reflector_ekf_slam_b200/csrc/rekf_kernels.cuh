@@ -389,6 +389,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   const bool has_gps = gps && gps[0] != 0.0 && MM > 0;   // the GPS rows live inside `if (MM > 0)` (gps.cc:246,305)
   const int r = MM > 0 ? 2 * MM + (has_gps ? 3 : 0) : 0;
 
+  pdl_trigger();                                   // k_innovation may be launched: it waits for this kernel's end in pdl_wait()
   // --- measurement rows: A_k (:272-273), B (:255), z − ẑ (:265-270), Q (:276) ----------------
   double *Hp = L.Hp + (size_t)s * L.rcap * 4;
   double *Hl = L.Hl + (size_t)s * L.rcap * 2;
@@ -458,6 +459,8 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
 // S = H·Σ·Hᵀ + Q (lower triangle) and the ν row
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_innovation(Layout L) {
+  pdl_trigger();
+  pdl_wait();
   timeline_mark(L, 2);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
@@ -888,6 +891,8 @@ __global__ void __launch_bounds__(256) k_solve_w(Layout L) {
 // Σ −= Wᵀ·W on the fp64 pipe: 64x64 tiles on/above the diagonal, upper elements only
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
+  pdl_trigger();
+  pdl_wait();
   timeline_mark(L, 5);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
@@ -950,6 +955,7 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
 // augmentation (:311-364) + end-of-step bookkeeping
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in_arg) {
+  pdl_wait();
   timeline_mark(L, 7);
   const InputRef in = resolve_input(in_arg);
   const int s = L.s0 + blockIdx.z;

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(256, 1) k_chol_trsm_rows(Layout L) {
 }
 
 __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
+  pdl_wait();
   timeline_mark(L, 4);
   extern __shared__ double sm_d[];
   const int s = L.s0 + blockIdx.z;
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(256, 2) k_solve_w3(Layout L) {
   REKF_WSTAMP();
 
   trsm_forward_tile(Y, Lp, Xs, Sb, L.Dinv + (size_t)s * (rld / kCholNb) * kCholNb * kCholNb, r, sld, rld);
+  pdl_trigger();
   REKF_WSTAMP();
 
   // ---- μ += Wᵀ·(L⁻¹ν) (:306), θ wrapped (:307); exact diagonal of the downdate -------------------------------

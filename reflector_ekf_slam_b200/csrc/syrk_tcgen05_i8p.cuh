@@ -130,12 +130,6 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
   int *sess_r = reinterpret_cast<int *>(fl_tab + 2 * 64);                                  // [kPMaxSess] r, 0 = nothing to do
   int *sess_n = sess_r + kPMaxSess;                                                        // [kPMaxSess] internal dimension
   volatile int4 *q_tile = reinterpret_cast<volatile int4 *>(sess_n + kPMaxSess);           // [kPQ] {session, i0, j0, flags}; session < 0: drained
-  for (int q = threadIdx.x; q < min(L.Sg, kPMaxSess); q += kPThreads) {
-    const SessionState &st = L.st[L.s0 + q];
-    sess_r[q] = (st.r > 0 && !st.exact_update) ? st.r : 0;
-    sess_n[q] = internal_dim(st.N);
-  }
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Tn64 = L.ld / kI8TileN;
   const int tiles = (L.ld / 128) * (L.ld / 128 + 1);     // 128x64 tiles on/above the diagonal, per session
@@ -152,6 +146,15 @@ k_syrk_tcgen05_i8p(Layout L, const __grid_constant__ CUtensorMap map_a, const __
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // barrier init and the TMEM allocation above overlap the tail of the kernel in front (programmatic dependent launch);
+  // everything below reads what the chain produced
+  pdl_trigger();
+  pdl_wait();
+  for (int q = threadIdx.x; q < min(L.Sg, kPMaxSess); q += kPThreads) {
+    const SessionState &st = L.st[L.s0 + q];
+    sess_r[q] = (st.r > 0 && !st.exact_update) ? st.r : 0;
+    sess_n[q] = internal_dim(st.N);
   }
   tc_fence_before();
   __syncthreads();
@@ -517,14 +520,24 @@ inline const char *syrk_i8p_init(SyrkI8P &tc, const Layout &L) {
   return nullptr;
 }
 
-inline int syrk_i8p_launch(const SyrkI8P &tc, const Layout &L, cudaStream_t stream) {
+inline int syrk_i8p_launch(const SyrkI8P &tc, const Layout &L, cudaStream_t stream, bool pdl = false) {
   if (!tc.ready) return -1;
   const int total = (L.ld / 128) * (L.ld / 128 + 1) * L.Sg;
   const int ctas = tc.num_sms - tc.reserve_sms > 1 ? tc.num_sms - tc.reserve_sms : 1;
   const int grid = total < ctas ? total : ctas;
-  if (tc.resident) k_syrk_tcgen05_i8p<true><<<grid, kPThreads, kPSmemRes, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
-  else k_syrk_tcgen05_i8p<false><<<grid, kPThreads, kPSmemStr, stream>>>(L, tc.map_a, tc.map_b, tc.map_sig);
-  return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kPThreads);
+  cfg.dynamicSmemBytes = tc.resident ? kPSmemRes : kPSmemStr;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // barrier init / TMEM allocation overlap the kernel in front
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const cudaError_t e = tc.resident ? cudaLaunchKernelEx(&cfg, k_syrk_tcgen05_i8p<true>, L, tc.map_a, tc.map_b, tc.map_sig)
+                                    : cudaLaunchKernelEx(&cfg, k_syrk_tcgen05_i8p<false>, L, tc.map_a, tc.map_b, tc.map_sig);
+  return e == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace rekf
