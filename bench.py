@@ -377,7 +377,7 @@ def adapter_leg(a, stream, k_state, k_pose):
         if res.returncode != 0:
             return {"error": "g++ failed: " + res.stderr[-300:]}
     nb = stream["n_build"]
-    T = nb + k_state + k_pose + 2
+    T = nb + 2 * k_state + k_pose + 2
     path = os.path.join(ROOT, "scripts", "bin", f"adapter_stream_{os.getpid()}.bin")
     with open(path, "wb") as f:
         f.write(struct.pack("4i", T, a.m, a.N, 0 if a.model == "diff" else 1))
@@ -399,6 +399,8 @@ def adapter_leg(a, stream, k_state, k_pose):
         "api": "ekf::ReflectorEKFSLAMB200 (C++11 adapter): HandleOdometryMessage, GetState(), HandleObservationMessage, GetState() per step — "
                "the node's pattern (ros_node.cc:515,638): a by-value State with the full n x n covariance after every message",
         "d2h_bytes_per_step": 2 * (n * n + n + 3) * 8,
+        "by_reference": {"value": d["state_steps"] / d["ref_seconds"], "steps": d["state_steps"], "d2h_bytes_per_step": 2 * (n * n + n + 3) * 8,
+                         "api": "same, GetStateVector() + GetCoviarance() (references to the refreshed, page-locked mirror: no by-value copy)"},
         "pose_only": {"value": d["pose_steps"] / d["pose_seconds"], "steps": d["pose_steps"], "d2h_bytes_per_step": 2 * 12 * 8,
                       "api": "same, GetPose() (pose + 3x3 block) in place of GetState()"},
     }
@@ -653,7 +655,7 @@ def run_b200(a):
         batch = None
         if not a.no_adapter:
             try:
-                adapter = adapter_leg(a, streams[0], 30 if a.config != "C4" else 4, 200 if a.config != "C4" else 20)
+                adapter = adapter_leg(a, streams[0], 30 if a.config != "C4" else 4, 140 if a.config != "C4" else 20)
             except Exception as e:
                 adapter = {"error": repr(e)}
         if not a.no_cpu_baseline:

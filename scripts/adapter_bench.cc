@@ -3,6 +3,8 @@
 // :421-561): HandleOdometryMessage, GetState(), HandleObservationMessage, GetState() — a full by-value State (mu and the
 // n x n covariance) after EVERY message, host buffers in, host buffers out.  Then the same stream with GetPose() in place
 // of GetState() (what a node that publishes pose + markers actually needs: 96 bytes per message instead of n² doubles).
+// A third pass reads the state through the by-REFERENCE getters (GetStateVector() / GetCoviarance(): the refreshed, page-locked
+// mirror, no by-value copy): what the full-covariance read costs without the interface's copy.
 // bench.py builds and runs this (`e2e_adapter`).  Usage: adapter_bench <stream.bin> <n_build> <k_state> <k_pose>
 // stream.bin: int32 {steps, m_stride, N, model}, then per step: double od[4], double t_obs, int32 cnt, float xy[2*m_stride].
 #define REKF_ADAPTER_STUB_TYPES
@@ -26,7 +28,7 @@ int main(int argc, char **argv)
   if (std::fread(hdr, sizeof(int32_t), 4, f) != 4) return 4;
   const int T = hdr[0], m = hdr[1];
   const int n_build = std::atoi(argv[2]), k_state = std::atoi(argv[3]), k_pose = std::atoi(argv[4]);
-  if (n_build + k_state + k_pose + 2 > T) return 5;
+  if (n_build + 2 * k_state + k_pose + 2 > T) return 5;
   std::vector<Step> steps(static_cast<size_t>(T));
   for (int k = 0; k < T; ++k)
   {
@@ -48,7 +50,8 @@ int main(int argc, char **argv)
   ekf::ReflectorEKFSLAMB200 *b200 = new ekf::ReflectorEKFSLAMB200(opt, hdr[2], m);
   std::unique_ptr<ekf::ReflectorEKFSLAMInterface> slam(b200);
   double sink = 0.;
-  auto run = [&](int k, bool full_state) {
+  auto run = [&](int k, int mode) {   // mode 1: GetState() by value, 0: GetPose(), 2: by-reference getters
+    const bool full_state = mode == 1;
     const Step &s = steps[k];
     sensor::OdometryData o;
     o.time = s.od[0];
@@ -57,26 +60,31 @@ int main(int argc, char **argv)
     double pose[3], cov[9];
     slam->HandleOdometryMessage(o);
     if (full_state) { ekf::State st = slam->GetState(); sink += st.mu(0) + st.sigma(0, 0); }   // ros_node.cc:638
+    else if (mode == 2) { sink += slam->GetStateVector()(0) + slam->GetCoviarance()(0, 0); }
     else { b200->GetPose(pose, cov); sink += pose[0] + cov[0]; }
     sensor::PointCloud cloud;
     for (int i = 0; i < s.cnt; ++i) cloud.push_back(Eigen::Vector2f(s.xy[2 * i], s.xy[2 * i + 1]));
     slam->HandleObservationMessage(sensor::Observation(s.t_obs, cloud));
     if (full_state) { ekf::State st = slam->GetState(); sink += st.mu(0) + st.sigma(0, 0); }   // ros_node.cc:515
+    else if (mode == 2) { sink += slam->GetStateVector()(0) + slam->GetCoviarance()(0, 0); }
     else { b200->GetPose(pose, cov); sink += pose[0] + cov[0]; }
   };
   int k = 0;
-  for (; k < n_build; ++k) run(k, false);          // map building (untimed)
-  run(k++, true);                                  // sizes and page-locks the mirror (untimed)
+  for (; k < n_build; ++k) run(k, 0);              // map building (untimed)
+  run(k++, 1);                                     // sizes and page-locks the mirror (untimed)
   typedef std::chrono::steady_clock clk;
   const clk::time_point t0 = clk::now();
-  for (int e = k + k_state; k < e; ++k) run(k, true);
+  for (int e = k + k_state; k < e; ++k) run(k, 1);
   const clk::time_point t1 = clk::now();
-  run(k++, false);
+  for (int e = k + k_state; k < e; ++k) run(k, 2);
+  const clk::time_point t1b = clk::now();
+  run(k++, 0);
   const clk::time_point t2 = clk::now();
-  for (int e = k + k_pose; k < e; ++k) run(k, false);
+  for (int e = k + k_pose; k < e; ++k) run(k, 0);
   const clk::time_point t3 = clk::now();
   const int n = static_cast<int>(slam->GetStateVector().rows());
-  std::printf("{\"n\": %d, \"state_steps\": %d, \"state_seconds\": %.6f, \"pose_steps\": %d, \"pose_seconds\": %.6f, \"sink\": %.3e}\n", n, k_state,
-              std::chrono::duration<double>(t1 - t0).count(), k_pose, std::chrono::duration<double>(t3 - t2).count(), sink);
+  std::printf("{\"n\": %d, \"state_steps\": %d, \"state_seconds\": %.6f, \"ref_seconds\": %.6f, \"pose_steps\": %d, \"pose_seconds\": %.6f, \"sink\": %.3e}\n", n,
+              k_state, std::chrono::duration<double>(t1 - t0).count(), std::chrono::duration<double>(t1b - t1).count(), k_pose,
+              std::chrono::duration<double>(t3 - t2).count(), sink);
   return 0;
 }
