@@ -15,7 +15,7 @@
 //     resident in shared memory; only the 64-row B boxes (16 KB per 64 K-bytes, 4-stage ring) stream per tile.  Per
 //     tile the SM pulls 64 KB (+128 KB / strip length) of int8 panels from L2 instead of 192 KB — the round-1 kernel
 //     was bound by exactly that L2→SM stream.  (K > 256 bytes, config C4: the panel does not fit; both operands stream
-//     through a 2-stage ring as before — template parameter kRes.)
+//     through a 4-stage ring — template parameter kRes.)
 //   * one CTA per SM pulls strips from a device-wide atomic cursor over the linearised tile order with guided
 //     self-scheduling (strip length = remaining / (2 x CTAs), clamped to [1, kPMaxStrip]): long strips while there is
 //     plenty of work, single tiles at the end, so the launch has no tail; a CTA that starts late — its SM was still
@@ -47,7 +47,7 @@ constexpr int kPChunkA = kI8Slices * kPBoxA;             // 32 KB: all four slic
 constexpr int kPChunkB = kI8Slices * kPBoxB;             // 16 KB
 constexpr int kPResChunks = 4;                           // resident A panel: K <= 256 bytes
 constexpr int kPResBStages = 4;                          // resident mode: B ring
-constexpr int kPStrStages = 2;                           // streaming mode: (A + B) ring
+constexpr int kPStrStages = 4;                           // streaming mode: (A + B) ring, 4 x 48 KB (2 stages left the MMA waiting for operands: C4 203 us)
 constexpr int kPTables = 2048;                           // barriers, scale/flag tables, session table, tile ring
 constexpr int kPSmemRes = kPResChunks * kPChunkA + kPResBStages * kPChunkB + kPSigSlots * kPSigBox + 1024 + kPTables;   // 227 KB exactly
 constexpr int kPSmemStr = kPStrStages * (kPChunkA + kPChunkB) + kPSigSlots * kPSigBox + 1024 + kPTables;
