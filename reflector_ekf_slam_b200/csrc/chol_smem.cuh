@@ -141,6 +141,7 @@ __device__ __forceinline__ void chol_trailing(double *A, const int *tab, const d
 // block of a split frame (nothing for frames that are not split).
 __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L, int part) {
   pdl_wait();
+  if (L.shadow) pdl_trigger();   // k_gather_y and k_solve_ll start beside this kernel (solve_ll.cuh): every block of it is resident by then
   timeline_mark(L, 3);
   extern __shared__ __align__(128) double sm_d[];
   const int s = L.s0 + blockIdx.x;
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
 
   const int jb_last = r - (nblk - 1) * kCholNb;             // true width of the last block
   for (int b = 0; b < nblk; ++b) {
-    if (b == nblk - 1) pdl_trigger();                       // the last block: the TRSM kernel may be launched (it waits in pdl_wait())
+    if (b == nblk - 1 && !L.shadow) pdl_trigger();          // the last block: the TRSM kernel may be launched (it waits in pdl_wait())
     const int J = b * kCholNb;
     const int lda = chol_lda(R1, b);
     double *P = A + chol_col_off(R1, b);                    // element (J + i, J + c) at P[c * lda + i]
@@ -310,6 +311,14 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
     // ---- phase 3: the panel's update of block column b+1 only (what the next diagonal block and its rows need);
     //      the rest of the trailing matrix is updated in the shadow of the next factorisation (phase 1) ------------
     chol_trailing(A, tab, P, lda, J, R1, r, 0, 3, warp, NW, lane);
+    if (L.sync && part == 0 && cb_b == b && b < nblk - 1) {
+      // warp b issued block column b's copies before phase 3: they have landed by now.  Complete → visible to the generic proxy →
+      // released: k_solve_ll may consume block column b, X_b (warp 0's stores of phase 1, ordered by the barriers since) and ν_b
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) sync_raise(L.sync + (size_t)s * L.sync_n + b);
+    }
     __syncthreads();
     REKF_TSTAMP();
   }
@@ -333,6 +342,12 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
   if (lane == 0) tlog[64 + warp] = (double)clock64();       // per-warp finish stamps
 #endif
   if (bad && lane == 0) atomicOr(&st.flags, FLAG_NOT_SPD);
+  if (L.sync && part == 0) {                                 // the last block column (and everything before it) is out
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) sync_raise(L.sync + (size_t)s * L.sync_n + nblk - 1);
+  }
+  timeline_mark(L, 9);
 }
 
 // ---- split frames, stage 3: S22 −= L21·L21ᵀ for rows / columns r1..r (row r = ν; its column does not exist), lower triangle.

@@ -34,7 +34,8 @@ enum : int {
   FLAG_LANDMARK_CAPACITY = 1,     // augmentation would exceed max_landmarks: extra reflectors dropped
   FLAG_NOT_SPD = 2,               // a pivot of S = HΣHᵀ+Q was not positive
   FLAG_OBS_CAPACITY = 4,          // more observations in a frame than max_observations
-  FLAG_TCGEN05_TIMEOUT = 8        // an mbarrier wait in the tensor-core SYRK gave up (should never happen)
+  FLAG_TCGEN05_TIMEOUT = 8,       // an mbarrier wait in the tensor-core SYRK gave up (should never happen)
+  FLAG_SYNC_TIMEOUT = 16          // k_solve_ll gave up waiting for a flag of the Cholesky / gather kernels (should never happen)
 };
 
 struct SessionState {
@@ -119,6 +120,11 @@ struct Layout {
   int *step;      // device step counter for replay (one per pipeline group)
   int *tile_counter;  // work-queue head of the persistent SYRK (one per pipeline group; reset by k_syrk_f64)
   unsigned *step_ticket;  // blocks of k_augment that have finished (one per pipeline group): the last one advances `step`
+  // cross-kernel pacing of the shadowed TRSM (solve_ll.cuh), [S][sync_n] ints cleared by k_observation_front every frame:
+  // [0..7] block column b of L (with X_b and ν_b) is in global memory; [8 + y·(ld/128) + x] rows 32y.. of Y, columns 128x.., are
+  int *sync;
+  int sync_n;
+  int shadow;     // the Cholesky, k_gather_y and k_solve_ll run as one programmatic-launch chain, each triggering at its start
   unsigned long long *tlog;  // optional kernel-start timeline (REKF_TIMELINE=1): [0] = entries used, then (globaltimer ns << 12 | kernel id << 8 | first session)
 };
 
@@ -139,6 +145,22 @@ __device__ __forceinline__ void timeline_mark(const Layout &L, int kernel_id) {
 // a dependent that wait for tens of microseconds would hold the SMs the other pipeline group needs.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// bounded wait for a flag another kernel raises (thread 0 of a CTA)
+__device__ __forceinline__ bool sync_wait(const int *flag) {
+  for (int it = 0; it < (1 << 21); ++it) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v) return true;
+    __nanosleep(200);
+  }
+  return false;
+}
+// raise a flag after this thread's (and, behind a barrier, its CTA's) global writes
+__device__ __forceinline__ void sync_raise(int *flag) {
+  __threadfence();
+  asm volatile("st.release.gpu.global.b32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+
 __host__ __device__ inline int round_up(int v, int g) { return (v + g - 1) / g * g; }
 // offset of Σ[i][j] in the upper-triangle-only storage
 __host__ __device__ __forceinline__ size_t sym_idx(int i, int j, int ld) {

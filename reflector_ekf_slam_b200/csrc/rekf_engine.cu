@@ -19,6 +19,7 @@
 #include "rekf_kernels.cuh"
 #include "chol_smem.cuh"
 #include "solve_w.cuh"
+#include "solve_ll.cuh"
 #include "syrk_exact_rows.cuh"
 #include "syrk_tcgen05.cuh"
 #include "syrk_tcgen05_i8.cuh"
@@ -104,6 +105,7 @@ struct rekf_handle {
   int prof_calls[K_COUNT]{};
   // tcgen05 SYRK resources
   bool chol_resident = false, solve_w2 = false;
+  bool solve_ll = false;       // the flag-paced left-looking TRSM (solve_ll.cuh) replaces k_solve_w3: frames always fit the resident Cholesky
   bool pdl = true;             // programmatic dependent launch along the step's kernel chain (REKF_PDL=0 turns it off)
   SyrkTc tc{};
   SyrkI8P tc8p{};
@@ -290,7 +292,8 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     const int g = (L.rcap + 15) / 16;
     CK(launch_chain(k_innovation, dim3(g, g, L.Sg), dim3(16, 16), 0, stream, h->pdl, L));
   }
-  if (h->solve_w2) CK(cudaEventRecord(grp.ev_fork, stream));
+  const bool shadow = L.shadow != 0;
+  if (h->solve_w2 && !shadow) CK(cudaEventRecord(grp.ev_fork, stream));
   {
     ProfScope p(h, K_CHOL, stream);
     if (h->chol_resident) {
@@ -311,7 +314,12 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
       k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L, 0);
     }
   }
-  if (h->solve_w2) {
+  if (shadow) {
+    // one programmatic-launch chain in this stream, Cholesky → gather → TRSM (launch_obs_wide), each triggering at its start:
+    // the three run side by side, paced by flags in global memory (solve_ll.cuh)
+    ProfScope p(h, K_GATHER, stream);
+    CK(launch_chain(k_gather_y, dim3(L.ld / 128, (L.rcap / 2 + kGYPairs - 1) / kGYPairs, L.Sg), dim3(256), 0, stream, true, L));
+  } else if (h->solve_w2) {
     // fork: Y = H·Σ needs only the match lists and the predicted Σ — a parallel branch (under capture: of the step graph) that
     // runs in the shadow of the Cholesky (one CTA per session, the rest of the GPU idle).  It is forked behind k_innovation
     // and issued after the Cholesky launch: beside k_innovation its ~1000 short blocks tripled that kernel's latency.
@@ -322,7 +330,7 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     }
     CK(cudaEventRecord(grp.ev_join, grp.side_stream));
   }
-  if (h->solve_w2) CK(cudaStreamWaitEvent(stream, grp.ev_join, 0));   // join before the TRSM
+  if (h->solve_w2 && !shadow) CK(cudaStreamWaitEvent(stream, grp.ev_join, 0));   // join before the TRSM
   CK(cudaGetLastError());
   return 0;
 }
@@ -333,7 +341,8 @@ int launch_obs_wide(rekf_handle *h, Group &grp, const InputRef &in) {
   cudaStream_t stream = grp.stream;
   {
     ProfScope p(h, K_SOLVE, stream);
-    if (h->solve_w2) CK(launch_chain(k_solve_w3, dim3(L.ld / kW3Cols, 1, L.Sg), dim3(256), smem_solve_w3(L.rld), stream, h->pdl && L.rcap <= kCholResidentMax, L));
+    if (h->solve_ll) CK(launch_chain(k_solve_ll, dim3(L.ld / kW3Cols, 1, L.Sg), dim3(kLLThreads), smem_solve_ll(), stream, h->pdl, L));
+    else if (h->solve_w2) CK(launch_chain(k_solve_w3, dim3(L.ld / kW3Cols, 1, L.Sg), dim3(256), smem_solve_w3(L.rld), stream, h->pdl && L.rcap <= kCholResidentMax, L));
     else k_solve_w<<<dim3(L.ld / kWCols, 1, L.Sg), 256, smem_solve(L), stream>>>(L);
   }
   if (h->opts.cov_update == REKF_COV_TCGEN05_I8X4) {
@@ -646,6 +655,16 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   if ((rc = dev_alloc(h, &L.tile_counter, G + 1))) return rc;
   if ((rc = dev_alloc(h, &L.step_ticket, G + 1))) return rc;
   if (std::getenv("REKF_TIMELINE") && (rc = dev_alloc(h, &L.tlog, kTimelineCap))) return rc;
+  // the TRSM in the shadow of the Cholesky (solve_ll.cuh): every frame fits the single-pass resident factorisation and the fp64
+  // W panel exists.  Side by side only along a programmatic-launch chain (one pipeline group); otherwise the same kernel, in order.
+  h->solve_ll = L.rcap <= kCholResidentMax && L.W64 != nullptr && smem_solve_w3(L.rld) <= 227 * 1024;
+  if (const char *e = std::getenv("REKF_SOLVE_LL")) h->solve_ll = h->solve_ll && std::atoi(e) != 0;
+  if (h->solve_ll) {
+    L.sync_n = 8 + (L.rld / kCholNb) * (L.ld / 128);
+    if ((rc = dev_alloc(h, &L.sync, S * L.sync_n))) return rc;
+    L.shadow = h->pdl ? 1 : 0;
+    if (const char *e = std::getenv("REKF_SHADOW")) L.shadow = (h->pdl && std::atoi(e) != 0) ? 1 : 0;
+  }
 
   // initial state: time, pose (:8-11)
   {
@@ -691,6 +710,10 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
     CK(cudaFuncSetAttribute(k_chol_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w3(L.rld)));
   }
   CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
+  if (h->solve_ll) {
+    CK(cudaFuncSetAttribute(k_solve_ll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_ll()));
+    CK(cudaFuncSetAttribute(k_solve_ll, cudaFuncAttributePreferredSharedMemoryCarveout, 100));   // four blocks per SM
+  }
   if (opts->cov_update == REKF_COV_TCGEN05_TF32X3) {
     const char *why = syrk_tc_init(h->tc, L);
     if (why) return fail(h, REKF_ERR_CUDA, "tcgen05 SYRK setup failed: %s", why);
@@ -886,6 +909,7 @@ int rekf_sync(rekf_handle *h) {
   for (int s = 0; s < h->L.S; ++s) {
     if (st[s].flags & FLAG_NOT_SPD) return fail(h, REKF_ERR_NOT_SPD, "session %d: innovation matrix not positive definite", s);
     if (st[s].flags & FLAG_TCGEN05_TIMEOUT) return fail(h, REKF_ERR_CUDA, "session %d: tcgen05 SYRK barrier timeout", s);
+    if (st[s].flags & FLAG_SYNC_TIMEOUT) return fail(h, REKF_ERR_CUDA, "session %d: TRSM gave up waiting for the Cholesky / gather flags", s);
     if (st[s].flags & (FLAG_LANDMARK_CAPACITY | FLAG_OBS_CAPACITY)) return fail(h, REKF_ERR_CAPACITY, "session %d: capacity exceeded (flags %d)", s, st[s].flags);
   }
   return REKF_OK;

@@ -217,6 +217,8 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   double2 *lmd = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(lmf + L.Ncap) + 15) & ~(uintptr_t)15);   // [Ncap], 16-byte aligned
   float2 *xys = reinterpret_cast<float2 *>(lmd + L.Ncap);                          // [mcap] this frame's observations
 
+  if (L.sync)                        // pacing flags of this frame's Cholesky / gather / TRSM (solve_ll.cuh)
+    for (int i = tid; i < L.sync_n; i += blockDim.x) L.sync[(size_t)s * L.sync_n + i] = 0;
   // ---- requests that do not depend on the message ------------------------------------------------------------
   constexpr int kPre = 2;           // columns per thread held in registers (covers Ncap <= 1022; the rest goes through a loop)
   double r0[kPre], r1[kPre], r2[kPre];
@@ -502,12 +504,13 @@ __global__ void __launch_bounds__(256) k_innovation(Layout L) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kGYPairs = 16;
 __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
+  if (L.shadow) pdl_trigger();   // link of the Cholesky → gather → TRSM chain (solve_ll.cuh); this kernel itself never waits
   timeline_mark(L, 8);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
   const int r = st.r;
   const int pair0 = blockIdx.y * kGYPairs;
-  if (r == 0 || 2 * pair0 >= r) return;
+  if (r == 0) return;
   const int n = internal_dim(st.N);
   const int ld = L.ld;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -517,14 +520,15 @@ __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
   const int *Hslot = L.Hslot + (size_t)s * L.rcap;
   double *Y = L.Ybuf + (size_t)s * L.rld * ld;
   const int cbase = blockIdx.x * 128;
-  if (cbase >= round_up(n, kSigmaTile)) return;
+  const bool work = 2 * pair0 < r && cbase < round_up(n, kSigmaTile);
   double p0[4], p1[4], p2[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int c = cbase + 32 * u + lane;
-    p0[u] = Sg[sym_idx(0, c, ld)]; p1[u] = Sg[sym_idx(1, c, ld)]; p2[u] = Sg[sym_idx(2, c, ld)];
+    p0[u] = p1[u] = p2[u] = 0.0;
+    if (work) { p0[u] = Sg[sym_idx(0, c, ld)]; p1[u] = Sg[sym_idx(1, c, ld)]; p2[u] = Sg[sym_idx(2, c, ld)]; }
   }
-  for (int pb = pair0 + warp; pb < pair0 + kGYPairs && 2 * pb < r; pb += 8) {
+  for (int pb = pair0 + warp; work && pb < pair0 + kGYPairs && 2 * pb < r; pb += 8) {
     const int q0 = 2 * pb, q1 = q0 + 1;
     const bool two = q1 < r;
     const int slot0 = Hslot[q0], slot1 = two ? Hslot[q1] : -1;
@@ -558,6 +562,10 @@ __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
         Y[(size_t)q1 * ld + c] = live ? y1 : 0.0;
       }
     }
+  }
+  if (L.sync) {                                    // this block's rows and columns of Y are out: k_solve_ll may read them
+    __syncthreads();
+    if (threadIdx.x == 0) sync_raise(L.sync + (size_t)s * L.sync_n + 8 + blockIdx.y * (ld / 128) + blockIdx.x);
   }
 }
 

@@ -6,8 +6,8 @@ sys.path.insert(0, ROOT)
 import torch
 from reflector_ekf_slam_b200.engine import EKFBatch
 from reflector_ekf_slam_b200.synth import make_stream
-S = 8
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+S = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 T = 30
 sts = [make_stream("C3", T, session=s) for s in range(S)]
 b = EKFBatch(S, max_landmarks=1024, max_observations=100, cov_update=2, use_graphs=1, pipeline_groups=G)
@@ -30,15 +30,15 @@ e = raw[1:1 + n]
 t = (e >> np.uint64(12)).astype(np.float64) / 1e3
 kid = ((e >> np.uint64(8)) & np.uint64(15)).astype(int)
 s0 = (e & np.uint64(255)).astype(int)
-names = ["odo", "front", "innov", "chol", "solve", "syrkf64", "syrk", "augment", "gather_y"] + ["?"] * 7
+names = ["odo", "front", "innov", "chol", "solve", "syrkf64", "syrk", "augment", "gather_y", "chol_end", "lastflag", "solve_end"] + ["?"] * 4
 order = np.argsort(t)
 t, kid, s0 = t[order], kid[order], s0[order]
-per_step = 8 * G   # kernels per step: front, gather_y, innov, chol, solve, syrkf64, syrk, augment
-sel = slice(len(t) - 3 * per_step, len(t))
+fronts = np.nonzero((kid == 1) & (s0 == 0))[0]        # group 0's front kernels: one per step
+sel = slice(fronts[-4], fronts[-1])
 t0 = t[sel][0]
 prev = {}
 for tt, k, g in zip(t[sel], kid[sel], s0[sel]):
     d = tt - prev.get(g, tt)
     prev[g] = tt
-    print(f"{tt - t0:9.1f} us  group@{g:<2d} {names[k]:8s} (+{d:6.1f} since this group's previous kernel start)")
-print("steps/s over the last 20 steps:", 20 * S / ((t[-1] - t[len(t) - 1 - 20 * per_step]) * 1e-6))
+    print(f"{tt - t0:9.1f} us  group@{g:<2d} {names[k]:8s} (+{d:6.1f} since this group's previous mark)")
+print("steps/s over the last 20 steps:", 20 * S / ((t[fronts[-1]] - t[fronts[-21]]) * 1e-6))
