@@ -261,6 +261,15 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
         Dg[jj * kCholNb + lane] = x[jj];
       }
     } else if (b > 0) {
+      if (L.sync && part == 0 && warp == 1 + (b - 1) % (NW - 1)) {
+        // this warp issued block column b-1's copies before phase 3: complete → visible to the generic proxy → released:
+        // k_solve_ll may consume block column b-1, X_{b-1} (warp 0's stores, ordered by the barriers since) and ν_{b-1}.
+        // Here, not at the end of phase 3: the wait would sit on the critical path there (measured: +6 µs per factorisation)
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) sync_raise(L.sync + (size_t)s * L.sync_n + b - 1);
+      }
       chol_trailing(A, tab, A + chol_col_off(R1, b - 1), chol_lda(R1, b - 1), J - kCholNb, R1, r, 4, 1 << 30, warp - 1, NW - 1, lane);
     }
     __syncthreads();
@@ -303,22 +312,17 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
     REKF_TSTAMP();
     // block column b of L is final: it goes back to global memory now, in the shadow of the remaining blocks (the last block
     // column waits for the ν fix-up after the loop)
-    if (cb_b == b && b < nblk - 1 && col_bytes) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
+    // (issued by a warp that is never the panel warp: it is also the one that later waits for the copies and tells k_solve_ll)
+    if (warp == 1 + b % (NW - 1) && b < nblk - 1) {
+      const unsigned bytes = (unsigned)((R1 - J + 1) & ~1) * 8u;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(Sb + (size_t)(J + lane) * sld + J),
+                   "r"((uint32_t)__cvta_generic_to_shared(P + lane * lda)), "r"(bytes) : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
 
     // ---- phase 3: the panel's update of block column b+1 only (what the next diagonal block and its rows need);
     //      the rest of the trailing matrix is updated in the shadow of the next factorisation (phase 1) ------------
     chol_trailing(A, tab, P, lda, J, R1, r, 0, 3, warp, NW, lane);
-    if (L.sync && part == 0 && cb_b == b && b < nblk - 1) {
-      // warp b issued block column b's copies before phase 3: they have landed by now.  Complete → visible to the generic proxy →
-      // released: k_solve_ll may consume block column b, X_b (warp 0's stores of phase 1, ordered by the barriers since) and ν_b
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) sync_raise(L.sync + (size_t)s * L.sync_n + b);
-    }
     __syncthreads();
     REKF_TSTAMP();
   }
@@ -330,13 +334,11 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
   // ---- publish the last block column of L (the others left inside the loop): the same per-column bulk copies, the other way ----
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes of the panels → visible to the bulk engine
   __syncthreads();
-  if (col_bytes) {
-    if (cb_b == nblk - 1) {
-      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's column (issued above or inside the loop) has landed
+  if (col_bytes && cb_b == nblk - 1) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(col_g), "r"((uint32_t)__cvta_generic_to_shared(col_s)), "r"(col_bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's copies (issued here or inside the loop) have landed
   REKF_TSTAMP();
 #ifdef REKF_CHOL_TIMING
   if (lane == 0) tlog[64 + warp] = (double)clock64();       // per-warp finish stamps

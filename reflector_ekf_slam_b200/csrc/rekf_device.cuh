@@ -109,6 +109,7 @@ struct Layout {
   float *Wt_hi, *Wt_lo;  // [S][ld][rld] tf32 hi/lo split of Wᵀ (K-major operands of the tcgen05 SYRK)
   double *W64;    // [S][rld][ld] fp64 W, measurement-row major: row k holds W[k][all slots] (fp64 SYRK and the exact rows; nullptr in tf32 mode)
   double *Ybuf;   // [S][rld][ld] Y = H·Σ, written by k_gather_y beside the Cholesky, read by k_solve_w3 as coalesced tiles
+                  // (k_solve_ll: scratch for the thread-private accumulated updates of the blocks below the current one)
   int8_t *Wq;     // [S][4][kq/64][ld][64] signed 7-bit digit slices of the row-scaled Wᵀ (REKF_COV_TCGEN05_I8X4), K in
                   // 64-byte chunks OUTSIDE the row index: a TMA box of 128 rows x 64 K-bytes is one contiguous 8 KB block
   int *Wexp;      // [S][ld] per-row power-of-two exponent e_c of Wq
@@ -121,10 +122,10 @@ struct Layout {
   int *tile_counter;  // work-queue head of the persistent SYRK (one per pipeline group; reset by k_syrk_f64)
   unsigned *step_ticket;  // blocks of k_augment that have finished (one per pipeline group): the last one advances `step`
   // cross-kernel pacing of the shadowed TRSM (solve_ll.cuh), [S][sync_n] ints cleared by k_observation_front every frame:
-  // [0..7] block column b of L (with X_b and ν_b) is in global memory; [8 + y·(ld/128) + x] rows 32y.. of Y, columns 128x.., are
+  // [b] block column b of L (with X_b and ν_b) is in global memory
   int *sync;
   int sync_n;
-  int shadow;     // the Cholesky, k_gather_y and k_solve_ll run as one programmatic-launch chain, each triggering at its start
+  int shadow;     // k_cholesky_smem → k_solve_ll is a programmatic-launch edge and the Cholesky triggers at its start: side by side
   unsigned long long *tlog;  // optional kernel-start timeline (REKF_TIMELINE=1): [0] = entries used, then (globaltimer ns << 12 | kernel id << 8 | first session)
 };
 

@@ -292,8 +292,8 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     const int g = (L.rcap + 15) / 16;
     CK(launch_chain(k_innovation, dim3(g, g, L.Sg), dim3(16, 16), 0, stream, h->pdl, L));
   }
-  const bool shadow = L.shadow != 0;
-  if (h->solve_w2 && !shadow) CK(cudaEventRecord(grp.ev_fork, stream));
+  const bool side_gather = h->solve_w2 && !h->solve_ll;   // k_solve_ll gathers Y = H·Σ itself (solve_ll.cuh)
+  if (side_gather) CK(cudaEventRecord(grp.ev_fork, stream));
   {
     ProfScope p(h, K_CHOL, stream);
     if (h->chol_resident) {
@@ -314,12 +314,7 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
       k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L, 0);
     }
   }
-  if (shadow) {
-    // one programmatic-launch chain in this stream, Cholesky → gather → TRSM (launch_obs_wide), each triggering at its start:
-    // the three run side by side, paced by flags in global memory (solve_ll.cuh)
-    ProfScope p(h, K_GATHER, stream);
-    CK(launch_chain(k_gather_y, dim3(L.ld / 128, (L.rcap / 2 + kGYPairs - 1) / kGYPairs, L.Sg), dim3(256), 0, stream, true, L));
-  } else if (h->solve_w2) {
+  if (side_gather) {
     // fork: Y = H·Σ needs only the match lists and the predicted Σ — a parallel branch (under capture: of the step graph) that
     // runs in the shadow of the Cholesky (one CTA per session, the rest of the GPU idle).  It is forked behind k_innovation
     // and issued after the Cholesky launch: beside k_innovation its ~1000 short blocks tripled that kernel's latency.
@@ -330,7 +325,7 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     }
     CK(cudaEventRecord(grp.ev_join, grp.side_stream));
   }
-  if (h->solve_w2 && !shadow) CK(cudaStreamWaitEvent(stream, grp.ev_join, 0));   // join before the TRSM
+  if (side_gather) CK(cudaStreamWaitEvent(stream, grp.ev_join, 0));   // join before the TRSM
   CK(cudaGetLastError());
   return 0;
 }
@@ -660,7 +655,7 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   h->solve_ll = L.rcap <= kCholResidentMax && L.W64 != nullptr && smem_solve_w3(L.rld) <= 227 * 1024;
   if (const char *e = std::getenv("REKF_SOLVE_LL")) h->solve_ll = h->solve_ll && std::atoi(e) != 0;
   if (h->solve_ll) {
-    L.sync_n = 8 + (L.rld / kCholNb) * (L.ld / 128);
+    L.sync_n = 8;
     if ((rc = dev_alloc(h, &L.sync, S * L.sync_n))) return rc;
     L.shadow = h->pdl ? 1 : 0;
     if (const char *e = std::getenv("REKF_SHADOW")) L.shadow = (h->pdl && std::atoi(e) != 0) ? 1 : 0;

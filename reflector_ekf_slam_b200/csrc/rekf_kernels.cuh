@@ -504,7 +504,6 @@ __global__ void __launch_bounds__(256) k_innovation(Layout L) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kGYPairs = 16;
 __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
-  if (L.shadow) pdl_trigger();   // link of the Cholesky → gather → TRSM chain (solve_ll.cuh); this kernel itself never waits
   timeline_mark(L, 8);
   const int s = L.s0 + blockIdx.z;
   const SessionState &st = L.st[s];
@@ -562,10 +561,6 @@ __global__ void __launch_bounds__(256) k_gather_y(Layout L) {
         Y[(size_t)q1 * ld + c] = live ? y1 : 0.0;
       }
     }
-  }
-  if (L.sync) {                                    // this block's rows and columns of Y are out: k_solve_ll may read them
-    __syncthreads();
-    if (threadIdx.x == 0) sync_raise(L.sync + (size_t)s * L.sync_n + 8 + blockIdx.y * (ld / 128) + blockIdx.x);
   }
 }
 
