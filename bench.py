@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--sessions", type=int, default=0, help="independent sessions per GPU (0: the configuration's default)")
-    ap.add_argument("--groups", type=int, default=2, help="pipeline groups the sessions of one GPU are split into (1: lock-step)")
+    ap.add_argument("--groups", type=int, default=1, help="pipeline groups the sessions of one GPU are split into (1: lock-step)")
     ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the persistent SYRK leaves to other groups (0: engine default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cov", default="i8", choices=["i8", "tcgen05", "f64"])

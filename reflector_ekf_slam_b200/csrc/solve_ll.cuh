@@ -37,7 +37,7 @@ constexpr int kLLBlk = 32 * kLLP;
 constexpr int kLLQP = 20;                // words per staged (digit plane, column) row of 64 K-bytes
 constexpr int kLLGP = 33;                // columns per row pair of the staged Σ values (+1: the fragment reads spread over the banks)
 
-inline size_t smem_solve_ll() { return sizeof(double) * (5 * kLLBlk + 4 * 32) + 64 * sizeof(int); }
+inline size_t smem_solve_ll() { return sizeof(double) * (5 * kLLBlk + 4 * 32) + (64 + kCholResidentMax) * sizeof(int); }
 
 __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
   if (!L.shadow) pdl_wait();
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
   double *sdiag = cstat + 96;                          // [32] prior Σ[c][c]
   int *sexp = reinterpret_cast<int *>(sdiag + 32);     // [32]
   int &s_ok = sexp[32];                                // every flag wait succeeded (thread 0's)
+  int *Hs = sexp + 64;                                 // [kCholResidentMax] landmark slot of every row of H
   const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   if (tid < 32) sdiag[tid] = Sg[(size_t)min(c0 + tid, ld - 1) * (ld + 1)];
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
     for (int u = 0; u < 4; ++u) {
       const int pair = nt + 4 * u, q0 = kCholNb * jb + 2 * pair, c = c0 + lane;
       double *dst = Gs + (size_t)(pair * kLLGP + lane) * 2;
-      const int slot = (q0 < r) ? __ldg(Hslot + q0) : -1;
+      const int slot = (q0 < r) ? Hs[q0] : -1;
       if (slot < 0) {
         dst[0] = 0.0; dst[1] = 0.0;
       } else if (slot > c) {
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
       const int q = kCholNb * jb + 8 * mt + g;
       y[mt][0] = y[mt][1] = 0.0;
       if (q < r) {
-        const int slot = __ldg(Hslot + q);
-        const bool staged = slot == __ldg(Hslot + (q & ~1));   // always, for the reference's row layout; kept general
+        const int slot = Hs[q];
+        const bool staged = slot == Hs[q & ~1];        // always, for the reference's row layout; kept general
         const double a0 = __ldg(Hp + 4 * q), a1 = __ldg(Hp + 4 * q + 1), a2 = __ldg(Hp + 4 * q + 2);
         const double l0 = __ldg(Hl + 2 * q), l1 = __ldg(Hl + 2 * q + 1);
 #pragma unroll
@@ -145,6 +146,8 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
 
   double pa[2] = {0.0, 0.0}, pd[2] = {0.0, 0.0}, pm[2] = {0.0, 0.0};   // this thread's columns: running sums over the rows
   double acc[4][2];                                    // Ỹ_J of the coming step
+  for (int q = tid; q < r; q += kLLThreads) Hs[q] = Hslot[q];
+  __syncthreads();
   issue_gather(0);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
@@ -212,9 +215,9 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
     }
     if (jb + 1 == nblk) break;
     __syncthreads();                                   // W_J is in shared memory
-    double wb[8];                                      // its B fragments for this warp's column tile
+    double wb[8];                                      // −W_J: its B fragments for this warp's column tile
 #pragma unroll
-    for (int ks = 0; ks < 8; ++ks) wb[ks] = Wt[(4 * ks + t4) * kLLP + 8 * nt + g];
+    for (int ks = 0; ks < 8; ++ks) wb[ks] = -Wt[(4 * ks + t4) * kLLP + 8 * nt + g];
     // ---- U_I −= L_IJ·W_J for the blocks below, the next diagonal block first (it stays in registers) --------------------
     for (int ib = jb + 1; ib < nblk; ++ib) {
       const int sg = (ib - jb - 1) & 1;
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
       for (int ks = 0; ks < 8; ++ks) {
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
-          dmma884(u[mt][0], u[mt][1], -Lc[(4 * ks + t4) * kLLP + 8 * mt + g], wb[ks], u[mt][0], u[mt][1]);
+          dmma884(u[mt][0], u[mt][1], Lc[(4 * ks + t4) * kLLP + 8 * mt + g], wb[ks], u[mt][0], u[mt][1]);
       }
       if (ib == jb + 1) {
 #pragma unroll

@@ -1,16 +1,16 @@
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/rl3_gputest.txt 2>&1; echo "rc=$?" >> gpurun_out/rl3_gputest.txt
-tail -4 gpurun_out/rl3_gputest.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/rl4_gputest.txt 2>&1; echo "rc=$?" >> gpurun_out/rl4_gputest.txt
+tail -4 gpurun_out/rl4_gputest.txt
 B="timeout 300 python bench.py --no-cpu-baseline --no-adapter --steps 200"
-$B --groups 1 > gpurun_out/rl3_g1.json 2> gpurun_out/rl3_g1.err
-$B --groups 2 > gpurun_out/rl3_g2.json 2> gpurun_out/rl3_g2.err
-REKF_SHADOW=0 $B --groups 1 > gpurun_out/rl3_g1_noshadow.json 2>/dev/null
-$B --groups 1 --sessions 4 > gpurun_out/rl3_s4g1.json 2>/dev/null
-$B --groups 1 --sessions 16 > gpurun_out/rl3_s16g1.json 2>/dev/null
-$B --groups 1 --sessions 32 > gpurun_out/rl3_s32g1.json 2>/dev/null
-$B --groups 1 --config C2 > gpurun_out/rl3_c2g1.json 2>/dev/null
-REKF_TIMELINE=1 timeout 200 python scripts/timeline.py 1 8 > gpurun_out/rl3_timeline_g1_s8.txt 2>&1
-REKF_TIMELINE=1 timeout 200 python scripts/timeline.py 1 1 > gpurun_out/rl3_timeline_g1_s1.txt 2>&1
-for f in gpurun_out/rl3_*.json; do python - "$f" <<'PY'
+$B --groups 1 > gpurun_out/rl4_g1.json 2> gpurun_out/rl4_g1.err
+$B --groups 2 > gpurun_out/rl4_g2.json 2> gpurun_out/rl4_g2.err
+REKF_SHADOW=0 $B --groups 1 > gpurun_out/rl4_g1_noshadow.json 2>/dev/null
+$B --groups 1 --sessions 4 > gpurun_out/rl4_s4g1.json 2>/dev/null
+$B --groups 1 --sessions 16 > gpurun_out/rl4_s16g1.json 2>/dev/null
+$B --groups 1 --sessions 32 > gpurun_out/rl4_s32g1.json 2>/dev/null
+$B --groups 1 --config C2 > gpurun_out/rl4_c2g1.json 2>/dev/null
+REKF_TIMELINE=1 timeout 200 python scripts/timeline.py 1 8 > gpurun_out/rl4_timeline_g1_s8.txt 2>&1
+REKF_TIMELINE=1 timeout 200 python scripts/timeline.py 1 1 > gpurun_out/rl4_timeline_g1_s1.txt 2>&1
+for f in gpurun_out/rl4_*.json; do python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads([l for l in open(sys.argv[1]) if l.startswith('{')][-1])
@@ -18,4 +18,4 @@ try:
 except Exception as e: print(sys.argv[1], 'ERR', e)
 PY
 done
-tail -12 gpurun_out/rl3_timeline_g1_s8.txt; tail -12 gpurun_out/rl3_timeline_g1_s1.txt
+tail -12 gpurun_out/rl4_timeline_g1_s8.txt; tail -12 gpurun_out/rl4_timeline_g1_s1.txt
