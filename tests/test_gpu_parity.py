@@ -330,6 +330,48 @@ def test_replay_device_matches_host_path(engine_lib):
     assert np.array_equal(outs[0], outs[1])
 
 
+@pytest.mark.parametrize("cov", ["i8", "f64"])
+def test_shadow_trsm_bitwise_and_parity(engine_lib, cov, monkeypatch):
+    """The TRSM that runs BESIDE the Cholesky (solve_ll.cuh: flags in global memory, programmatic launch chain) against the
+    same kernel run in order (REKF_SHADOW=0: every flag is up before it starts): bit-identical state after every step, and
+    both inside the north-star bar against the oracle.  N=120, m=40: r = 80 = three 32-row blocks (diagonal products, trailing
+    updates, thread-private update storage, the gather one block ahead); then 3 steps at C3 (seven blocks, 68 tiles)."""
+    from oracle.pyoracle import STRUCTURED, Oracle
+    from reflector_ekf_slam_b200.engine import ReflectorEKFSLAM
+    from reflector_ekf_slam_b200.synth import DIFF, make_stream
+
+    def engines(**kw):
+        out = []
+        for shadow in ("0", "1"):
+            monkeypatch.setenv("REKF_SHADOW", shadow)    # read when the handle is created
+            out.append(ReflectorEKFSLAM(cov_update=COV_MODES[cov], **kw))
+        monkeypatch.delenv("REKF_SHADOW")
+        return out
+
+    st = make_stream(None, 12, N=120, m=40, model=DIFF, seed=77)
+    in_order, shadow = engines(odom_model=st["model"], max_landmarks=120, max_observations=40)
+    orc = Oracle(algebra=STRUCTURED, odom_model=st["model"])
+    for k in range(len(st["odom"])):
+        drive_engine(in_order, st, k)
+        drive_engine(shadow, st, k)
+        drive_oracle(orc, st, k)
+        assert np.array_equal(shadow.GetStateVector(), in_order.GetStateVector()), f"step {k}"
+        if k % 3 == 0 or k == len(st["odom"]) - 1:
+            assert np.array_equal(shadow.GetCoviarance(), in_order.GetCoviarance()), f"step {k}"
+            compare_matches(shadow, orc, f"shadow step {k}")
+            compare_state(shadow, orc, tag=f"shadow/{cov} step {k}")
+    assert shadow.error_flags() == 0 and in_order.error_flags() == 0
+
+    st = make_stream("C3", 3)
+    in_order, shadow = engines(max_landmarks=1024, max_observations=100)
+    for k in range(len(st["odom"])):
+        drive_engine(in_order, st, k)
+        drive_engine(shadow, st, k)
+    assert np.array_equal(shadow.GetStateVector(), in_order.GetStateVector())
+    assert np.array_equal(shadow.GetCoviarance(), in_order.GetCoviarance())
+    assert shadow.error_flags() == 0 and len(shadow.match_result()[0]) == 100
+
+
 @pytest.mark.parametrize("groups", [2, 3])
 def test_pipeline_groups_bitwise(engine_lib, groups):
     """pipeline_groups > 1 (each group of sessions on its own stream, persistent SYRK fed from the atomic tile queue)
