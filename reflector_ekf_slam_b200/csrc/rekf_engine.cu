@@ -63,6 +63,8 @@ struct Group {
   struct StepGraphs {
     cudaGraphExec_t step = nullptr;          // whole step, or its latency-bound half when the groups are staggered
     cudaGraphExec_t wide = nullptr;          // staggered groups: the bandwidth-bound half (TRSM, SYRK, augmentation)
+    cudaGraphExec_t multi = nullptr;         // one group: kMultiSteps steps in one graph (replay): the programmatic-launch chain runs
+                                             // across step boundaries and the graph-to-graph gap is paid once per kMultiSteps steps
     InputRef in{};
     int64_t launches = 0;                    // kernel nodes per step
   } replay_gs, host_gs;
@@ -285,7 +287,7 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
   cudaStream_t stream = grp.stream;
   {
     ProfScope p(h, K_FRONT, stream);
-    k_observation_front<<<L.Sg, 1024, smem_front(L), stream>>>(L, in);
+    CK(launch_chain(k_observation_front, dim3(L.Sg), dim3(1024), smem_front(L), stream, h->pdl, L, in));
   }
   {
     ProfScope p(h, K_INNOV, stream);
@@ -378,10 +380,12 @@ int launch_observation(rekf_handle *h, Group &grp, const InputRef &in) {
 
 // (re)capture the fused step chain of one group for the inputs `in` (k_observation_front takes the odometry message,
 // k_augment advances the replay counter)
-int capture_step(rekf_handle *h, Group &g, const InputRef &in, Group::StepGraphs &gs) {
+constexpr int kMultiSteps = 4;
+int capture_step(rekf_handle *h, Group &g, const InputRef &in, Group::StepGraphs &gs, bool want_multi = false) {
   if (gs.step && std::memcmp(&in, &gs.in, sizeof(InputRef)) == 0 && (gs.wide != nullptr) == staggered(h, g)) return 0;
   if (gs.step) { cudaGraphExecDestroy(gs.step); gs.step = nullptr; }
   if (gs.wide) { cudaGraphExecDestroy(gs.wide); gs.wide = nullptr; }
+  if (gs.multi) { cudaGraphExecDestroy(gs.multi); gs.multi = nullptr; }
   const bool split = staggered(h, g);          // two graphs, so that the stagger events sit between them
   const int64_t before = h->launches;
   for (int part = 0; part < (split ? 2 : 1); ++part) {
@@ -400,6 +404,18 @@ int capture_step(rekf_handle *h, Group &g, const InputRef &in, Group::StepGraphs
   }
   gs.in = in;
   gs.launches = h->launches - before;          // kernel nodes per step
+  if (want_multi && !split && h->pdl) {
+    cudaGraph_t cg = nullptr;
+    CK(cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int k = 0; k < kMultiSteps && !rc; ++k) rc = launch_observation(h, g, in);
+    cudaError_t ce = cudaStreamEndCapture(g.stream, &cg);
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(h, REKF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+    CK(cudaGraphInstantiate(&gs.multi, cg, 0));
+    cudaGraphDestroy(cg);
+    CK(cudaGraphUpload(gs.multi, g.stream));
+  }
   h->launches = before;                        // the capture pass itself launched nothing
   return 0;
 }
@@ -503,6 +519,7 @@ int init_group(rekf_handle *h, Group &g, int s0, int Sg, int index, cudaStream_t
 
 void destroy_group(Group &g) {
   for (Group::StepGraphs *gs : {&g.replay_gs, &g.host_gs}) {
+    if (gs->multi) cudaGraphExecDestroy(gs->multi);
     if (gs->step) cudaGraphExecDestroy(gs->step);
     if (gs->wide) cudaGraphExecDestroy(gs->wide);
   }
@@ -876,11 +893,19 @@ int rekf_replay_device(rekf_handle *h, const void *d_odom, const void *d_obs_tim
     CK(cudaMemcpyAsync(g.replay_in_dev, &in, sizeof(InputRef), cudaMemcpyHostToDevice, g.stream));
     InputRef via{};
     via.indirect = g.replay_in_dev;
-    int rc = capture_step(h, g, via, g.replay_gs);
+    int rc = capture_step(h, g, via, g.replay_gs, true);
     if (rc) return rc;
   }
   // groups are issued round-robin; each one's stream orders its own steps, nothing orders groups against each other
-  for (int t = 0; t < T; ++t) {
+  int t_first = 0;
+  if (graphs && act.size() == 1 && act[0]->replay_gs.multi) {   // one group: kMultiSteps steps per graph launch
+    Group &g = *act[0];
+    for (; t_first + kMultiSteps <= T; t_first += kMultiSteps) {
+      CK(cudaGraphLaunch(g.replay_gs.multi, g.stream));
+      h->launches += g.replay_gs.launches * kMultiSteps;
+    }
+  }
+  for (int t = t_first; t < T; ++t) {
     for (size_t gi = 0; gi < act.size(); ++gi) {
       Group &g = *act[gi];
       if (graphs) {

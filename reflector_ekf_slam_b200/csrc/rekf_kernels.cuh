@@ -201,6 +201,7 @@ struct FrontShared {
 };
 
 __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in_arg) {
+  pdl_wait();                        // inside a multi-step graph: the previous step's k_augment is complete
   timeline_mark(L, 1);
   extern __shared__ int sm_i[];
   __shared__ FrontShared fs;
@@ -959,6 +960,7 @@ __global__ void __launch_bounds__(256) k_syrk_f64(Layout L) {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in_arg) {
   pdl_wait();
+  pdl_trigger();                     // the next step's k_observation_front may be launched (it waits in pdl_wait())
   timeline_mark(L, 7);
   const InputRef in = resolve_input(in_arg);
   const int s = L.s0 + blockIdx.z;
@@ -1029,13 +1031,20 @@ __global__ void __launch_bounds__(256) k_augment(Layout L, InputRef in_arg) {
       }
     }
   }
-  // last block of this session commits the new size and publishes the pose
-  __threadfence();
-  __shared__ bool last;
-  if (threadIdx.x == 0) last = (atomicAdd(&st.ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
+  // The last block of this session commits the new size and publishes the pose.  Steady state (no new reflectors): nothing
+  // was written, so block 0 commits at once — no ticket, no fences (each a ~1 µs round trip on the step's critical path).
+  bool commit;
+  if (N2 > 0 || overflow) {
     __threadfence();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicAdd(&st.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    commit = last && threadIdx.x == 0;
+    if (commit) __threadfence();
+  } else {
+    commit = blockIdx.x == 0 && threadIdx.x == 0;
+  }
+  if (commit) {
     st.N = N + N2;
     if (overflow) st.flags |= FLAG_LANDMARK_CAPACITY;
     st.ticket = 0;
