@@ -30,7 +30,7 @@ e = raw[1:1 + n]
 t = (e >> np.uint64(12)).astype(np.float64) / 1e3
 kid = ((e >> np.uint64(8)) & np.uint64(15)).astype(int)
 s0 = (e & np.uint64(255)).astype(int)
-names = ["odo", "front", "innov", "chol", "solve", "syrkf64", "syrk", "augment", "gather_y", "chol_end", "lastflag", "solve_end"] + ["?"] * 4
+names = ["odo", "front", "innov", "chol", "solve", "syrkf64", "syrk", "augment", "gather_y", "chol_end", "lastflag", "solve_end", "?", "?", "?", "?"]
 order = np.argsort(t)
 t, kid, s0 = t[order], kid[order], s0[order]
 fronts = np.nonzero((kid == 1) & (s0 == 0))[0]        # group 0's front kernels: one per step
