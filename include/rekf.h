@@ -98,7 +98,10 @@ typedef struct rekf_options {
   int pipeline_groups;           /* batch handles only: split the S sessions into this many groups, each advancing on
                                     its own stream, so that one group's latency-bound kernels (association, Cholesky)
                                     overlap another group's bandwidth-bound ones (TRSM, covariance SYRK).  Sessions
-                                    never interact, so results are bit-identical to 1.  0 or 1: one group. */
+                                    never interact, so results are bit-identical to 1.  0 or 1: one group — the fast
+                                    setting: with one group the triangular solve runs beside the Cholesky on a
+                                    programmatic-launch chain, which covers the same idle time without a second
+                                    group competing for the SMs. */
   int syrk_reserve_sms;          /* with pipeline_groups > 1: SMs the persistent covariance SYRK leaves free for the
                                     other groups' kernels (0: default) */
 } rekf_options;
