@@ -195,7 +195,7 @@ private:
       if (flags != 0)
       {
         std::fprintf(stderr, "[rekf_b200] device flags 0x%x (1: landmark capacity exceeded, 2: S not positive definite, 4: observation "
-                             "capacity exceeded, 8: tensor-kernel timeout) - the filter no longer follows the reference\n", flags);
+                             "capacity exceeded, 8: tensor-kernel timeout, 16: solve/Cholesky hand-shake timeout) - the filter no longer follows the reference\n", flags);
         std::exit(-1);
       }
       if (rc == REKF_ERR_CAPACITY && n_now >= 3 && n_now != n)

@@ -70,3 +70,7 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(engine_lib):
     sass = subprocess.run([exe, "-sass", lib], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "UTCIMMA", "UTMALDG.5D", "UTMAREDG.3D.ADD", "UBLKCP", "LDTM", "DMMA"):
         assert mnemonic in sass, mnemonic
+    # the TRSM that runs beside the Cholesky (solve_ll.cuh): fp64 tensor pipe, cp.async staging, the bounded flag poll
+    body = sass.split("k_solve_ll", 1)[1].split("Function :", 1)[0]
+    for mnemonic in ("DMMA", "LDGSTS", "NANOSLEEP"):
+        assert mnemonic in body, mnemonic
