@@ -75,16 +75,21 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
                : "=d"(d0), "=d"(d1) : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
 
-// 1/sqrt(d) for a pivot of an SPD matrix, branch-free: the hardware's 23-bit seed (MUFU.RSQ64H) and two Newton steps (46, then
-// > 53 bits).  libdevice's rsqrt() carries special-case branches; inside the fully unrolled pivot loop they end the basic
-// block, and the scheduler could no longer start the next pivot's chain under the current column's rank-1 update — the
-// diagonal blocks ran at ~240 cycles per column instead of the ~130 of the dependent chain.
+// 1/sqrt(d) for a pivot of an SPD matrix, branch-free: the hardware's 23-bit seed (MUFU.RSQ64H) and kNewton Newton steps
+// (one: ~1e-13, two: full double).  libdevice's rsqrt() carries special-case branches; inside the fully unrolled pivot loop they
+// end the basic block, and the scheduler could no longer start the next pivot's chain under the current column's rank-1 update —
+// the diagonal blocks ran at ~240 cycles per column instead of the ~130 of the dependent chain.
+// The second step is three dependent fp64 operations on the factorisation's serial spine (200 pivots per frame at C3: 2 µs of
+// 57).  The tensor-core covariance modes resolve the downdate to 2^-29 of a row scale anyway and take ONE step (the factor then
+// satisfies S = L·Lᵀ to ~2e-13 relative instead of 2e-16; measured on the 80-step C3 run: see DESIGN.md §5); the fp64 mode — the
+// engine's own reference mode — keeps two.
+template <int kNewton>
 __device__ __forceinline__ double pivot_rsqrt(double d) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
   const double h = 0.5 * d;
   y = y * fma(-h * y, y, 1.5);
-  y = y * fma(-h * y, y, 1.5);
+  if (kNewton > 1) y = y * fma(-h * y, y, 1.5);
   return y;
 }
 
@@ -139,6 +144,7 @@ __device__ __forceinline__ void chol_trailing(double *A, const int *tab, const d
 
 // part 0: the whole matrix (frames with r <= kCholResidentMax; larger frames: nothing).  part 1 / 2: the leading / trailing
 // block of a split frame (nothing for frames that are not split).
+template <int kNewton>
 __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L, int part) {
   pdl_wait();
   if (L.shadow) pdl_trigger();   // k_gather_y and k_solve_ll start beside this kernel (solve_ll.cuh): every block of it is resident by then
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(kCholSmemThreads, 1) k_cholesky_smem(Layout L,
 #pragma unroll
       for (int j = 0; j < kCholNb; ++j) {
         bad |= !(d > 0.0);
-        const double inv = pivot_rsqrt(d);
+        const double inv = pivot_rsqrt<kNewton>(d);
         const double l = (lane == j) ? d * inv : a[j] * inv;
         if (lane == j) rinv[j] = inv;
         if (j + 1 < kCholNb) d = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);   // next pivot, early

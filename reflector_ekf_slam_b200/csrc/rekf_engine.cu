@@ -107,6 +107,7 @@ struct rekf_handle {
   int prof_calls[K_COUNT]{};
   // tcgen05 SYRK resources
   bool chol_resident = false, solve_w2 = false;
+  int chol_newton = 2;         // Newton steps of the pivot rsqrt (chol_smem.cuh): 1 in the tensor-core covariance modes, 2 in fp64
   bool solve_ll = false;       // the flag-paced left-looking TRSM (solve_ll.cuh) replaces k_solve_w3: frames always fit the resident Cholesky
   bool pdl = true;             // programmatic dependent launch along the step's kernel chain (REKF_PDL=0 turns it off)
   SyrkTc tc{};
@@ -300,15 +301,16 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
     ProfScope p(h, K_CHOL, stream);
     if (h->chol_resident) {
       const size_t sm = smem_chol_resident(std::min(L.rcap, kCholResidentMax));
-      CK(launch_chain(k_cholesky_smem, dim3(L.Sg), dim3(kCholSmemThreads), sm, stream, h->pdl, L, 0));
+      auto chol = h->chol_newton == 1 ? k_cholesky_smem<1> : k_cholesky_smem<2>;
+      CK(launch_chain(chol, dim3(L.Sg), dim3(kCholSmemThreads), sm, stream, h->pdl, L, 0));
       if (L.rcap > kCholResidentMax) {
         // two-level factorisation of frames with more rows than one SM holds (chol_smem.cuh); every stage decides on the
         // device whether the frame is split, so the chain is static
-        k_cholesky_smem<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 1);
+        chol<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 1);
         k_chol_trsm_rows<<<dim3((L.rcap - 32 + kW3Cols - 1) / kW3Cols, 1, L.Sg), 256, smem_solve_w3(L.rld), stream>>>(L);
         const int nt = (L.rcap + 1 + 31) / 32;
         k_chol_syrk<<<dim3(nt * (nt + 1) / 2, 1, L.Sg), 256, 0, stream>>>(L);
-        k_cholesky_smem<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 2);
+        chol<<<L.Sg, kCholSmemThreads, sm, stream>>>(L, 2);
         k_cholesky<<<L.Sg, 1024, smem_chol(L), stream>>>(L, 1);      // frames too large even for two levels
         h->launches += 5;
       }
@@ -669,6 +671,8 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   if (std::getenv("REKF_TIMELINE") && (rc = dev_alloc(h, &L.tlog, kTimelineCap))) return rc;
   // the TRSM in the shadow of the Cholesky (solve_ll.cuh): every frame fits the single-pass resident factorisation and the fp64
   // W panel exists.  Side by side only along a programmatic-launch chain (one pipeline group); otherwise the same kernel, in order.
+  h->chol_newton = opts->cov_update == REKF_COV_SIMT_F64 ? 2 : 1;
+  if (const char *e = std::getenv("REKF_CHOL_NEWTON")) h->chol_newton = std::atoi(e) == 1 ? 1 : 2;
   h->solve_ll = L.rcap <= kCholResidentMax && L.W64 != nullptr && smem_solve_w3(L.rld) <= 227 * 1024;
   if (const char *e = std::getenv("REKF_SOLVE_LL")) h->solve_ll = h->solve_ll && std::atoi(e) != 0;
   if (h->solve_ll) {
@@ -718,7 +722,8 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   // the resident Cholesky (one or two levels) and the DMMA TRSM come as a pair: both need the operands of a frame in one SM
   h->chol_resident = h->solve_w2;
   if (h->chol_resident) {
-    CK(cudaFuncSetAttribute(k_cholesky_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(std::min(L.rcap, kCholResidentMax))));
+    CK(cudaFuncSetAttribute(k_cholesky_smem<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(std::min(L.rcap, kCholResidentMax))));
+    CK(cudaFuncSetAttribute(k_cholesky_smem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chol_resident(std::min(L.rcap, kCholResidentMax))));
     CK(cudaFuncSetAttribute(k_chol_trsm_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve_w3(L.rld)));
   }
   CK(cudaFuncSetAttribute(k_solve_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_solve(L)));
