@@ -12,7 +12,7 @@
 //     Y[q][c] = A_q·Σ[0:3][c] + B_q·Σ[slot:slot+2][c], upper-triangle storage read through sym_idx) — no gather kernel, no Y buffer;
 //     the accumulated updates U_I (Ỹ_I = Y_I + U_I) are THREAD-PRIVATE: a thread owns the same 8 elements of every block (its
 //     DMMA accumulator fragment), keeps them in Layout::Ybuf between steps and re-reads only its own stores — no fences;
-//   * nothing but staging in shared memory (46 KB: two L blocks, X_J, Ỹ_J / W_J, the next block's Σ values), so FOUR CTAs fit an SM and the 544 column tiles
+//   * nothing but staging in shared memory (49 KB: two L blocks, X_J, Ỹ_J / W_J, the next block's Σ values and H rows), so FOUR CTAs fit an SM and the 544 column tiles
 //     of 8 sessions are all resident at once beside the 8 Cholesky CTAs (the resident-tile kernel needs 113 KB: two waves at 8
 //     sessions, the second one after the factorisation); W goes to Layout::W64 (the fp64 panel the exact paths consume anyway)
 //     block by block and is re-read from L2 for the int8 digit slices once the row scales are known;
@@ -37,7 +37,7 @@ constexpr int kLLBlk = 32 * kLLP;
 constexpr int kLLQP = 20;                // words per staged (digit plane, column) row of 64 K-bytes
 constexpr int kLLGP = 33;                // columns per row pair of the staged Σ values (+1: the fragment reads spread over the banks)
 
-inline size_t smem_solve_ll() { return sizeof(double) * (5 * kLLBlk + 4 * 32) + (64 + kCholResidentMax) * sizeof(int); }
+inline size_t smem_solve_ll() { return sizeof(double) * (5 * kLLBlk + 4 * 32 + 32 * 6) + (64 + kCholResidentMax) * sizeof(int); }
 
 __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
   if (!L.shadow) pdl_wait();
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
   int *sexp = reinterpret_cast<int *>(sdiag + 32);     // [32]
   int &s_ok = sexp[32];                                // every flag wait succeeded (thread 0's)
   int *Hs = sexp + 64;                                 // [kCholResidentMax] landmark slot of every row of H
+  double *Hr = reinterpret_cast<double *>(Hs + kCholResidentMax);   // [32][6] coefficients of the NEXT block's rows: A_q (3), pad, B_q (2)
   const int tid = threadIdx.x, lane = tid & 31, nt = tid >> 5;
   const int g = lane >> 2, t4 = lane & 3;
   if (tid < 32) sdiag[tid] = Sg[(size_t)min(c0 + tid, ld - 1) * (ld + 1)];
@@ -110,6 +111,10 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 1)), "l"(Sg + sym_idx(slot + 1, c, ld)) : "memory");
       }
     }
+    if (tid < 96) {                                    // the rows' coefficients: Hp[q][0..3] as two 16-byte halves, Hl[q][0..1] as one
+      const int row = tid / 3, part = tid - 3 * row, q = kCholNb * jb + row;
+      if (q < r) cp16(Hr + row * 6 + 2 * part, part < 2 ? Hp + 4 * q + 2 * part : Hl + 2 * q);
+    }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   double p0[2], p1[2], p2[2];
@@ -126,8 +131,8 @@ __global__ void __launch_bounds__(kLLThreads, 4) k_solve_ll(Layout L) {
       if (q < r) {
         const int slot = Hs[q];
         const bool staged = slot == Hs[q & ~1];        // always, for the reference's row layout; kept general
-        const double a0 = __ldg(Hp + 4 * q), a1 = __ldg(Hp + 4 * q + 1), a2 = __ldg(Hp + 4 * q + 2);
-        const double l0 = __ldg(Hl + 2 * q), l1 = __ldg(Hl + 2 * q + 1);
+        const double *hr = Hr + (8 * mt + g) * 6;
+        const double a0 = hr[0], a1 = hr[1], a2 = hr[2], l0 = hr[4], l1 = hr[5];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int c = cme + e;
