@@ -107,6 +107,7 @@ struct rekf_handle {
   int prof_calls[K_COUNT]{};
   // tcgen05 SYRK resources
   bool chol_resident = false, solve_w2 = false;
+  int front_cluster = 4;       // CTAs per session in k_observation_front (a thread-block cluster shares the association; REKF_FRONT_CLUSTER)
   int chol_newton = 2;         // Newton steps of the pivot rsqrt (chol_smem.cuh): 1 in the tensor-core covariance modes, 2 in fp64
   bool solve_ll = false;       // the flag-paced left-looking TRSM (solve_ll.cuh) replaces k_solve_w3: frames always fit the resident Cholesky
   bool pdl = true;             // programmatic dependent launch along the step's kernel chain (REKF_PDL=0 turns it off)
@@ -251,6 +252,26 @@ cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
+// the same with thread-block clusters of `cluster_x` CTAs along x (grid.x a multiple of it)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, int cluster_x,
+                                 Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 
 size_t smem_chol(const Layout &L) { return sizeof(double) * ((size_t)(L.rcap + 1) * kPS + (size_t)kCholNb * kPS); }
 size_t smem_solve(const Layout &L) { return sizeof(double) * (size_t)L.rld * kYS; }
@@ -288,7 +309,10 @@ int launch_obs_narrow(rekf_handle *h, Group &grp, const InputRef &in) {
   cudaStream_t stream = grp.stream;
   {
     ProfScope p(h, K_FRONT, stream);
-    CK(launch_chain(k_observation_front, dim3(L.Sg), dim3(1024), smem_front(L), stream, h->pdl, L, in));
+    if (h->front_cluster > 1)
+      CK(launch_chain_cluster(k_observation_front, dim3(L.Sg * h->front_cluster), dim3(1024), smem_front(L), stream, h->pdl, h->front_cluster, L, in));
+    else
+      CK(launch_chain(k_observation_front, dim3(L.Sg), dim3(1024), smem_front(L), stream, h->pdl, L, in));
   }
   {
     ProfScope p(h, K_INNOV, stream);
@@ -671,6 +695,7 @@ static int create_batch_impl(const rekf_options *opts, int sessions, rekf_handle
   if (std::getenv("REKF_TIMELINE") && (rc = dev_alloc(h, &L.tlog, kTimelineCap))) return rc;
   // the TRSM in the shadow of the Cholesky (solve_ll.cuh): every frame fits the single-pass resident factorisation and the fp64
   // W panel exists.  Side by side only along a programmatic-launch chain (one pipeline group); otherwise the same kernel, in order.
+  if (const char *e = std::getenv("REKF_FRONT_CLUSTER")) h->front_cluster = std::max(1, std::min(8, std::atoi(e)));
   h->chol_newton = opts->cov_update == REKF_COV_SIMT_F64 ? 2 : 1;
   if (const char *e = std::getenv("REKF_CHOL_NEWTON")) h->chol_newton = std::atoi(e) == 1 ? 1 : 2;
   h->solve_ll = L.rcap <= kCholResidentMax && L.W64 != nullptr && smem_solve_w3(L.rld) <= 227 * 1024;

@@ -14,6 +14,7 @@
 // H has at most five non-zeros per row (3 pose columns + the landmark's 2, :272-275), so H·Σ is a gather
 // of five rows of Σ per measurement row and is never materialised outside shared memory.
 #pragma once
+#include <cooperative_groups.h>
 #include "rekf_device.cuh"
 #include "syrk_exact_rows.cuh"
 
@@ -198,6 +199,8 @@ struct FrontShared {
   const float *xy;
   const double *gps;
   int counts[3];
+  double P[9], vt[3];     // the predicted 3x3 block and the latched velocity: written to global memory after the cluster barrier
+  int vt_latched;
 };
 
 __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in_arg) {
@@ -205,7 +208,13 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   timeline_mark(L, 1);
   extern __shared__ int sm_i[];
   __shared__ FrontShared fs;
-  const int s = L.s0 + blockIdx.x;
+  // A cluster of kFrontCluster CTAs per session shares the association (the 10^5 distance tests are instruction-bound on one
+  // SM: 8 of this kernel's 15 µs): every CTA walks the (read-only) serial chain and stages the landmark means itself, takes
+  // every kFrontCluster-th observation and writes its decisions into rank 0's shared memory; rank 0 alone writes global state —
+  // the predicted pose block only AFTER the cluster barrier, so that no other rank can read it half-updated — and goes on.
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+  const int rank = (int)cluster.block_rank(), nrank = (int)cluster.num_blocks();   // 0 / 1 without a cluster launch
+  const int s = L.s0 + blockIdx.x / nrank;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int ld = L.ld;
   SessionState &st = L.st[s];
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   double2 *lmd = reinterpret_cast<double2 *>((reinterpret_cast<uintptr_t>(lmf + L.Ncap) + 15) & ~(uintptr_t)15);   // [Ncap], 16-byte aligned
   float2 *xys = reinterpret_cast<float2 *>(lmd + L.Ncap);                          // [mcap] this frame's observations
 
-  if (L.sync)                        // pacing flags of this frame's Cholesky / gather / TRSM (solve_ll.cuh)
+  if (L.sync && rank == 0)           // pacing flags of this frame's Cholesky / gather / TRSM (solve_ll.cuh)
     for (int i = tid; i < L.sync_n; i += blockDim.x) L.sync[(size_t)s * L.sync_n + i] = 0;
   // ---- requests that do not depend on the message ------------------------------------------------------------
   constexpr int kPre = 2;           // columns per thread held in registers (covers Ncap <= 1022; the rest goes through a loop)
@@ -227,11 +236,11 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   for (int u = 0; u < kPre; ++u) {
     const int c = kPoseSlots + tid + u * 1024;
     r0[u] = r1[u] = r2[u] = 0.0;
-    if (c < L.ncap) { r0[u] = Sg[c]; r1[u] = Sg[(size_t)ld + c]; r2[u] = Sg[(size_t)2 * ld + c]; }
+    if (c < L.ncap && rank == 0) { r0[u] = Sg[c]; r1[u] = Sg[(size_t)ld + c]; r2[u] = Sg[(size_t)2 * ld + c]; }
   }
   for (int j = tid; j < L.Ncap; j += blockDim.x) {          // slots past the live N hold zeros: harmless
     const double2 l = *reinterpret_cast<const double2 *>(mu + kPoseSlots + 2 * j);
-    lmd[j] = l;
+    if (rank == 0) lmd[j] = l;
     lmf[j] = make_float2((float)l.x, (float)l.y);
   }
 
@@ -252,6 +261,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
     fs.flags0 = st.flags;
     fs.g[0] = fs.g[1] = 0.0;
     fs.has_odom = 0;
+    fs.vt_latched = 0;
     if (in.fuse_odom) {                            // replay / step call: this step's HandleOdometryMessage first (:208-223)
       const double t_od = msg[0];
       if (!(t_od < t_state)) {                     // :211 stale messages are dropped
@@ -261,15 +271,14 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
         fs.has_odom = 1;
         predict_pose_block(t, P, pose);
         t_state = t_od;
-        st.vt[0] = vt[0]; st.vt[1] = vt[1]; st.vt[2] = vt[2];
+        fs.vt_latched = 1;
       }
     }
     const MotionTerms t = motion_model(L, vt, pose[2], t_obs - t_state);   // :232-233, no sign check on dt
     fs.g[2] = t.g02; fs.g[3] = t.g12;
     predict_pose_block(t, P, pose);
-    for (int i = 0; i < 3; ++i)
-      for (int j = i; j < 3; ++j) Sg[(size_t)i * ld + j] = P[i * 3 + j];
-    mu[0] = pose[0]; mu[1] = pose[1]; mu[2] = pose[2];
+    for (int i = 0; i < 9; ++i) fs.P[i] = P[i];
+    fs.vt[0] = vt[0]; fs.vt[1] = vt[1]; fs.vt[2] = vt[2];
     fs.pose[0] = pose[0]; fs.pose[1] = pose[1]; fs.pose[2] = pose[2];
     sincos(pose[2], &fs.sn, &fs.cs);
     int flag_add = 0;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
 
   // ---- both predicts on rows 0 and 1 (the mirrored columns are not stored) ---------------------------------------
   const int n = fs.n, N = fs.N, m = fs.m;
-  {
+  if (rank == 0) {
     const double ga0 = fs.g[0], ga1 = fs.g[1], gb0 = fs.g[2], gb1 = fs.g[3];
     const bool has_odom = fs.has_odom != 0;
 #pragma unroll
@@ -318,8 +327,9 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
   }
   const double px = fs.pose[0], py = fs.pose[1], th = fs.pose[2], sn = fs.sn, cs = fs.cs;
 
-  // --- ReflectorMatch: one warp per observation, lanes stride over landmarks -------------------
-  for (int i = warp; i < m; i += nwarps) {
+  // --- ReflectorMatch: one warp per observation, lanes stride over landmarks; this CTA takes observations rank, rank + nrank, … -
+  int *kind0 = cluster.map_shared_rank(kind, 0), *target0 = cluster.map_shared_rank(target, 0);
+  for (int i = rank + nrank * warp; i < m; i += nrank * nwarps) {
     // point_transformed_to_global_frame (:389-393): double arithmetic, float32 result
     const float2 o = xys[i];
     const double ox = (double)o.x, oy = (double)o.y;
@@ -359,9 +369,16 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
       warp_argmin(best, bj);
       if (sqrt(best) < 0.6) { k = kMatchState; tgt = bj; }                         // :446
     }
-    if (lane == 0) { kind[i] = k; target[i] = tgt; }
+    if (lane == 0) { kind0[i] = k; target0[i] = tgt; }
   }
-  __syncthreads();
+  cluster.sync();                                  // every rank's decisions are in rank 0's shared memory
+  if (rank != 0) return;
+  if (tid == 0) {                                  // the chain's global writes, now that no other rank reads the old values
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) Sg[(size_t)i * ld + j] = fs.P[i * 3 + j];
+    mu[0] = fs.pose[0]; mu[1] = fs.pose[1]; mu[2] = fs.pose[2];
+    if (fs.vt_latched) { st.vt[0] = fs.vt[0]; st.vt[1] = fs.vt[1]; st.vt[2] = fs.vt[2]; }
+  }
 
   // --- ordered compaction: lists keep observation order like the push_backs at :422/:448/:452.  One warp per list kind:
   //     ballot over 32 observations at a time, position = running count + popc of the lower lanes ----------------------
