@@ -205,6 +205,9 @@ struct FrontShared {
 
 __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRef in_arg) {
   pdl_wait();                        // inside a multi-step graph: the previous step's k_augment is complete
+  // first phase of the cluster barrier: a CTA's shared memory may only be written from another CTA once that CTA has started.
+  // Arrive here, wait just before the first remote store (the chain and the staging lie in between: nobody actually waits)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   timeline_mark(L, 1);
   extern __shared__ int sm_i[];
   __shared__ FrontShared fs;
@@ -329,6 +332,7 @@ __global__ void __launch_bounds__(1024, 1) k_observation_front(Layout L, InputRe
 
   // --- ReflectorMatch: one warp per observation, lanes stride over landmarks; this CTA takes observations rank, rank + nrank, … -
   int *kind0 = cluster.map_shared_rank(kind, 0), *target0 = cluster.map_shared_rank(target, 0);
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // every CTA of the cluster is running
   for (int i = rank + nrank * warp; i < m; i += nrank * nwarps) {
     // point_transformed_to_global_frame (:389-393): double arithmetic, float32 result
     const float2 o = xys[i];
