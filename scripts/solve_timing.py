@@ -1,5 +1,6 @@
 """Per-phase cycle counts of k_solve_w3, CTA 0 (build with REKF_NVCC_EXTRA=-DREKF_SOLVE_TIMING)."""
 import os, sys
+os.environ.setdefault("REKF_SOLVE_LL", "0")   # the instrumented kernel is the previous-generation k_solve_w3
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))

@@ -1,6 +1,7 @@
 """All cycle stamps of k_solve_w3, CTA 0 of session 0, with S sessions running side by side
 (build with REKF_NVCC_EXTRA="-DREKF_SOLVE_TIMING -DREKF_SOLVE_TIMING2").  usage: solve_timing2.py [S]"""
 import os, sys
+os.environ.setdefault("REKF_SOLVE_LL", "0")   # the instrumented kernel is the previous-generation k_solve_w3
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
